@@ -1,0 +1,125 @@
+/* zlb.h — thin C ABI between the host-side libzling mirror (C++ shim in libzling_b200/csrc/zl_api.cpp, or any
+ * FFI: ctypes / cgo / JNI) and the sm_100a CUDA block pipeline.  Plain C types only; no exceptions cross this
+ * boundary; every function returns 0 / a non-negative count on success and a negative zlb_status on failure,
+ * with a human-readable message retrievable through zlb_last_error().  There is NO CPU fallback: when no CUDA
+ * device (or no driver) is present zlb_create() fails with ZLB_E_NODEVICE.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference tree):
+ *   zlb_encoder_begin / zlb_encode_blocks / zlb_encoder_end
+ *        the per-16-MiB-block body of baidu::zling::Encode()            src/libzling.cpp:187-284
+ *        (ZlingRolzEncoder::Reset/Encode                                src/libzling_lz.cpp:128-316,
+ *         frequency count + ZlingMakeLengthTable/ZlingMakeEncodeTable   src/libzling.cpp:219-229,
+ *                                                                       src/libzling_huffman.cpp:41-138,
+ *         nibble header + ZlingCodebuf bit packing + level feedback     src/libzling.cpp:232-266,
+ *         framing flag/encpos/rlen/olen/payload/stop                    src/libzling.cpp:200,269-278)
+ *   zlb_decoder_begin / zlb_decode_blocks / zlb_decoder_end
+ *        the per-block body of baidu::zling::Decode()                   src/libzling.cpp:301-420
+ *        (Huffman LUT decode :347-402, ZlingRolzDecoder::Reset/Decode   src/libzling_lz.cpp:318-399)
+ *   zlb_encoder_get_state / zlb_encoder_set_state
+ *        the state that outlives a block in the reference: m_mtf[256]   src/libzling_lz.h:105 (never reset) and
+ *        current_level                                                  src/libzling.cpp:185,261-266
+ * The stream-lifetime objects (zlb_encoder / zlb_decoder) exist because of that carried state: blocks of ONE
+ * stream must be submitted in order; independent streams use independent encoder objects.
+ */
+#ifndef ZLB_H
+#define ZLB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZLB_BLOCK_BYTES      16777216u  /* kBlockSizeIn       src/libzling.cpp:70 */
+#define ZLB_SUBBLOCK_SYMBOLS 262144u    /* kBlockSizeRolz     src/libzling.cpp:71 */
+#define ZLB_SUBBLOCK_BYTES   393216u    /* kBlockSizeHuffman  src/libzling.cpp:72 */
+#define ZLB_STATE_BYTES      65540u     /* 256x256 MTF rank->byte tables + int32 current level */
+
+typedef enum {
+    ZLB_OK          = 0,
+    ZLB_E_ARG       = -1,   /* bad argument (NULL, level outside 0..4, unaligned block submission ...) */
+    ZLB_E_NODEVICE  = -2,   /* no CUDA device / driver: the product path refuses to run on the CPU */
+    ZLB_E_CUDA      = -3,   /* a CUDA runtime call or kernel failed; see zlb_last_error() */
+    ZLB_E_NOMEM     = -4,   /* host or device allocation failed */
+    ZLB_E_OVERFLOW  = -5,   /* caller's output buffer too small */
+    ZLB_E_FORMAT    = -6    /* malformed compressed stream (where the reference throws std::runtime_error) */
+} zlb_status;
+
+typedef struct zlb_ctx     zlb_ctx;      /* one per (process, GPU): device buffers, streams */
+typedef struct zlb_encoder zlb_encoder;  /* one per stream being encoded */
+typedef struct zlb_decoder zlb_decoder;  /* one per stream being decoded */
+
+/* ---- device / context ------------------------------------------------------------------------------- */
+int          zlb_device_count(void);                 /* number of CUDA devices, 0 if none, never fails */
+zlb_ctx*     zlb_create(int device, int max_blocks); /* buffers for up to max_blocks 16 MiB blocks per call */
+void         zlb_destroy(zlb_ctx* ctx);
+int          zlb_max_blocks(const zlb_ctx* ctx);
+const char*  zlb_last_error(void);                   /* thread-local message of the last failure */
+const char*  zlb_version(void);
+
+/* page-locked host buffers (faster H2D/D2H for zlb_encode_blocks / zlb_decode_blocks); plain malloc'd memory
+ * is accepted everywhere as well */
+void*        zlb_host_alloc(size_t bytes);
+void         zlb_host_free(void* p);
+
+/* upper bound of the compressed size of n input bytes (for sizing `out`) */
+size_t       zlb_encode_bound(size_t n);
+
+/* ---- encode ------------------------------------------------------------------------------------------ */
+zlb_encoder* zlb_encoder_begin(zlb_ctx* ctx, int level);   /* level 0..4 (src/libzling_lz.cpp:129-135) */
+void         zlb_encoder_end(zlb_encoder* enc);
+
+/* Encode n consecutive stream bytes held in HOST memory.  n must be a multiple of ZLB_BLOCK_BYTES except for
+ * the final call of a stream, and n <= max_blocks * ZLB_BLOCK_BYTES.  Writes the framed bytes of exactly these
+ * blocks (sub-block records + one stop byte per block) to out[0..*out_len).  Includes H2D and D2H copies. */
+int zlb_encode_blocks(zlb_encoder* enc, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* Same, but `d_in` / `d_out` are DEVICE pointers on the context's GPU (inputs already resident in HBM, output
+ * left in HBM); only the per-sub-block size table crosses PCIe.  d_in must be 16-byte aligned and readable for
+ * 16 bytes past n. */
+int zlb_encode_blocks_device(zlb_encoder* enc, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len);
+
+/* carried state: 65536 bytes of MTF tables (context-major, rank -> byte) followed by int32 LE current level */
+int zlb_encoder_get_state(zlb_encoder* enc, uint8_t* state /* ZLB_STATE_BYTES */);
+int zlb_encoder_set_state(zlb_encoder* enc, const uint8_t* state);
+
+/* ---- decode ------------------------------------------------------------------------------------------ */
+zlb_decoder* zlb_decoder_begin(zlb_ctx* ctx);
+void         zlb_decoder_end(zlb_decoder* dec);
+
+/* Decode whole framed blocks held in HOST memory: `in` must start at a block start (a 0x01 flag) and contain
+ * only complete blocks (each ending with its 0x00 stop flag), at most max_blocks of them.  *consumed = bytes of
+ * `in` used, *out_len = decoded bytes written. */
+int zlb_decode_blocks(zlb_decoder* dec, const uint8_t* in, size_t n, size_t* consumed, uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* ---- instrumentation (bench.py, tests) ------------------------------------------------------------------ */
+typedef struct {
+    double   ms_total;        /* device time of the last encode/decode call, first to last kernel (CUDA events) */
+    double   ms_parse;        /* zl_rolz_parse (dominant kernel) */
+    double   ms_mtf;
+    double   ms_huff_build;
+    double   ms_pack;
+    double   ms_h2d, ms_d2h;
+    uint32_t launches;        /* kernels launched by the last call */
+    uint32_t parse_launches;
+    uint32_t reparsed_blocks; /* blocks parsed again because the level-feedback prediction was wrong */
+    uint64_t tokens;          /* tokens produced by the last call */
+    uint64_t subblocks;
+} zlb_stats;
+int zlb_get_stats(const zlb_ctx* ctx, zlb_stats* out);
+
+/* intermediates of the last zlb_encode_blocks* call, for parity tests against the oracle:
+ *   tokens of block `blk`: u32 per token = sym | aux<<10 | byte<<22 | raw<<31 (sym: literals carry the MTF rank after the
+ *   call, aux = match idx or literal context), and the sub-block table (encpos_end, rlen, olen, level, ntok) */
+typedef struct { uint32_t tok_begin, tok_end, enc_begin, enc_end, rlen, level, olen, bits_lo; } zlb_subblock;
+int zlb_debug_tokens(zlb_ctx* ctx, int blk, uint32_t* tok, size_t cap, size_t* ntok);
+int zlb_debug_subblocks(zlb_ctx* ctx, int blk, zlb_subblock* sub, size_t cap, size_t* nsub);
+
+/* run only the Huffman table kernels on caller-supplied frequency tables (nsym = 514/cap 15 or 32/cap 8) */
+int zlb_debug_huff_tables(zlb_ctx* ctx, const uint32_t* freq, int ntables, int nsym, int cap, uint8_t* len_out, uint16_t* code_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZLB_H */

@@ -1,0 +1,286 @@
+"""ctypes binding of the C ABI (include/zlb.h) — what a Python user of the reference would call.
+
+The reference has no Python layer; this mirrors its C++ surface one to one so that tests read like the
+reference's usage (README.md:40-60: Encode(inputter, outputter, level) / Decode(inputter, outputter)):
+
+    ctx = Context(device=0, max_blocks=8)
+    z   = ctx.encode(data, level=2)        # baidu::zling::Encode  (src/libzling.cpp:174)
+    raw = ctx.decode(z)                    # baidu::zling::Decode  (src/libzling.cpp:293)
+
+There is no CPU fallback: a missing library or a missing CUDA device raises RuntimeError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+BLOCK = 16777216
+_u8p = C.POINTER(C.c_uint8)
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_double), ("ms_parse", C.c_double), ("ms_mtf", C.c_double), ("ms_huff_build", C.c_double),
+                ("ms_pack", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("launches", C.c_uint32),
+                ("parse_launches", C.c_uint32), ("reparsed_blocks", C.c_uint32), ("tokens", C.c_uint64), ("subblocks", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class SubBlock(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("tok_begin", "tok_end", "enc_begin", "enc_end", "rlen", "level", "olen", "bits_lo")]
+
+
+EXPORTS = ["zlb_device_count", "zlb_create", "zlb_destroy", "zlb_max_blocks", "zlb_last_error", "zlb_version",
+           "zlb_host_alloc", "zlb_host_free", "zlb_encode_bound", "zlb_encoder_begin", "zlb_encoder_end",
+           "zlb_encode_blocks", "zlb_encode_blocks_device", "zlb_encoder_get_state", "zlb_encoder_set_state",
+           "zlb_decoder_begin", "zlb_decoder_end", "zlb_decode_blocks", "zlb_get_stats", "zlb_debug_tokens",
+           "zlb_debug_subblocks", "zlb_debug_huff_tables"]
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """load libzling.so (built in-tree by libzling_b200.build); raises if it is missing — never falls back"""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError("libzling_b200: %s not built (run `python -m libzling_b200.build`); there is no CPU fallback" % path)
+    L = C.CDLL(path)
+    L.zlb_create.restype = C.c_void_p
+    L.zlb_create.argtypes = [C.c_int, C.c_int]
+    L.zlb_destroy.argtypes = [C.c_void_p]
+    L.zlb_max_blocks.argtypes = [C.c_void_p]
+    L.zlb_last_error.restype = C.c_char_p
+    L.zlb_version.restype = C.c_char_p
+    L.zlb_host_alloc.restype = C.c_void_p
+    L.zlb_host_alloc.argtypes = [C.c_size_t]
+    L.zlb_host_free.argtypes = [C.c_void_p]
+    L.zlb_encode_bound.restype = C.c_size_t
+    L.zlb_encode_bound.argtypes = [C.c_size_t]
+    L.zlb_encoder_begin.restype = C.c_void_p
+    L.zlb_encoder_begin.argtypes = [C.c_void_p, C.c_int]
+    L.zlb_encoder_end.argtypes = [C.c_void_p]
+    for f in (L.zlb_encode_blocks, L.zlb_encode_blocks_device):
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_encoder_get_state.argtypes = [C.c_void_p, _u8p]
+    L.zlb_encoder_set_state.argtypes = [C.c_void_p, _u8p]
+    L.zlb_decoder_begin.restype = C.c_void_p
+    L.zlb_decoder_begin.argtypes = [C.c_void_p]
+    L.zlb_decoder_end.argtypes = [C.c_void_p]
+    L.zlb_decode_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.zlb_debug_tokens.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_debug_subblocks.argtypes = [C.c_void_p, C.c_int, C.POINTER(SubBlock), C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_debug_huff_tables.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, _u8p, C.POINTER(C.c_uint16)]
+    _lib = L
+    return L
+
+
+class ZlingError(RuntimeError):
+    pass
+
+
+class FormatError(ZlingError, ValueError):
+    """malformed compressed stream — where the reference throws std::runtime_error (src/libzling.cpp:316-407)"""
+
+
+def _check(rc):
+    if rc < 0:
+        msg = load().zlb_last_error().decode()
+        raise (FormatError if rc == -6 else ZlingError)("zlb error %d: %s" % (rc, msg))
+
+
+def _as_u8(data):
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+class PinnedBuffer:
+    """page-locked host memory exposed as a numpy uint8 array"""
+
+    def __init__(self, nbytes):
+        L = load()
+        self._p = L.zlb_host_alloc(nbytes)
+        if not self._p:
+            raise ZlingError(L.zlb_last_error().decode())
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self._p))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            load().zlb_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """one GPU's block pipeline (zlb_ctx).  max_blocks 16 MiB blocks are processed per device call."""
+
+    def __init__(self, device=0, max_blocks=8):
+        L = load()
+        if L.zlb_device_count() <= 0:
+            raise ZlingError("libzling_b200: no CUDA device visible; this library has no CPU path")
+        self._h = L.zlb_create(device, max_blocks)
+        if not self._h:
+            raise ZlingError(L.zlb_last_error().decode())
+        self.device, self.max_blocks = device, max_blocks
+
+    def close(self):
+        if self._h:
+            load().zlb_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- whole-stream helpers (the shape of baidu::zling::Encode / Decode over in-memory buffers) -------
+    def encode(self, data, level=0):
+        enc = Encoder(self, level)
+        try:
+            a = _as_u8(data)
+            parts = []
+            step = self.max_blocks * BLOCK
+            for off in range(0, a.size, step):
+                parts.append(enc.encode_blocks(a[off:off + step]))
+            return b"".join(parts)
+        finally:
+            enc.close()
+
+    def decode(self, data, size_hint=None):
+        dec = Decoder(self)
+        try:
+            a = _as_u8(data)
+            parts, at = [], 0
+            while at < a.size:
+                used, raw = dec.decode_blocks(a[at:])
+                parts.append(raw)
+                at += used
+            return b"".join(parts)
+        finally:
+            dec.close()
+
+    def stats(self):
+        s = Stats()
+        _check(load().zlb_get_stats(self._h, C.byref(s)))
+        return s.asdict()
+
+    # -- intermediates of the last encode call (parity tests) -------------------------------------------
+    def debug_tokens(self, blk):
+        L = load()
+        n = C.c_size_t(0)
+        _check(L.zlb_debug_tokens(self._h, blk, None, 0, C.byref(n)))
+        out = np.zeros(max(n.value, 1), dtype=np.uint32)
+        _check(L.zlb_debug_tokens(self._h, blk, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size, C.byref(n)))
+        return out[:n.value]
+
+    def debug_subblocks(self, blk):
+        L = load()
+        arr = (SubBlock * 80)()
+        n = C.c_size_t(0)
+        _check(L.zlb_debug_subblocks(self._h, blk, arr, 80, C.byref(n)))
+        return [{k: getattr(arr[i], k) for k, _ in SubBlock._fields_} for i in range(n.value)]
+
+    def debug_huff_tables(self, freq, cap):
+        f = np.ascontiguousarray(freq, dtype=np.uint32)
+        nt, ns = f.shape
+        lens = np.zeros((nt, ns), dtype=np.uint8)
+        codes = np.zeros((nt, ns), dtype=np.uint16)
+        _check(load().zlb_debug_huff_tables(self._h, f.ctypes.data_as(C.POINTER(C.c_uint32)), nt, ns, cap,
+                                            lens.ctypes.data_as(_u8p), codes.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return lens, codes
+
+
+class Encoder:
+    """one stream being encoded (zlb_encoder): carries the MTF tables and the level-feedback flag across calls"""
+
+    def __init__(self, ctx, level=0):
+        L = load()
+        self.ctx = ctx
+        self._h = L.zlb_encoder_begin(ctx._h, level)
+        if not self._h:
+            raise ZlingError(L.zlb_last_error().decode())
+        self._out = None
+
+    def close(self):
+        if self._h:
+            load().zlb_encoder_end(self._h)
+            self._h = None
+
+    def encode_blocks(self, data, out=None):
+        """host buffers in, framed bytes out (copies included).  `data`: whole 16 MiB blocks except at stream end"""
+        a = _as_u8(data)
+        L = load()
+        cap = L.zlb_encode_bound(a.size)
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        n = C.c_size_t(0)
+        _check(L.zlb_encode_blocks(self._h, a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(n)))
+        return out[:n.value].tobytes()
+
+    def encode_blocks_into(self, a, out):
+        """like encode_blocks but writes into a caller buffer (e.g. pinned) and returns the byte count"""
+        n = C.c_size_t(0)
+        _check(load().zlb_encode_blocks(self._h, a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(n)))
+        return n.value
+
+    def encode_blocks_device(self, d_in_ptr, nbytes, d_out_ptr, out_cap):
+        """device pointers (e.g. torch tensors' data_ptr()); returns the byte count left in d_out"""
+        n = C.c_size_t(0)
+        _check(load().zlb_encode_blocks_device(self._h, d_in_ptr, nbytes, d_out_ptr, out_cap, C.byref(n)))
+        return n.value
+
+    def get_state(self):
+        s = np.zeros(65540, dtype=np.uint8)
+        _check(load().zlb_encoder_get_state(self._h, s.ctypes.data_as(_u8p)))
+        return s
+
+    def set_state(self, s):
+        s = np.ascontiguousarray(s, dtype=np.uint8)
+        assert s.size == 65540
+        _check(load().zlb_encoder_set_state(self._h, s.ctypes.data_as(_u8p)))
+
+
+class Decoder:
+    def __init__(self, ctx):
+        L = load()
+        self.ctx = ctx
+        self._h = L.zlb_decoder_begin(ctx._h)
+        if not self._h:
+            raise ZlingError(L.zlb_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().zlb_decoder_end(self._h)
+            self._h = None
+
+    def decode_blocks(self, data):
+        """decodes as many complete blocks as fit (<= max_blocks); returns (compressed bytes used, raw bytes)"""
+        a = _as_u8(data)
+        out = np.empty(self.ctx.max_blocks * BLOCK, dtype=np.uint8)
+        used, n = C.c_size_t(0), C.c_size_t(0)
+        _check(load().zlb_decode_blocks(self._h, a.ctypes.data, a.size, C.byref(used), out.ctypes.data, out.size, C.byref(n)))
+        return used.value, out[:n.value].tobytes()

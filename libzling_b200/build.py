@@ -1,0 +1,44 @@
+"""Builds libzling_b200/libzling.so IN-TREE with nvcc for sm_100a: CUDA kernels + host engine + C ABI (include/zlb.h)
++ the C++ drop-in API (include/libzling/libzling.h).  Cross-compiles without a GPU."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libzling.so")
+SOURCES = ["zl_engine.cu", "zl_api.cpp"]
+DEPS = SOURCES + ["zl_kernels.cu", "zl_kernels.cuh", "zl_tables.h", "../../include/zlb.h",
+                  "../../include/libzling/libzling.h", "../../include/libzling/libzling_utils.h"]
+
+
+def nvcc_path():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC,-fvisibility=default", "-shared", "-cudart", "static", "-o", LIB]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -1,0 +1,241 @@
+// Host-side mirror of the reference's public API (src/libzling.h:44-45, src/libzling_utils.{h,cpp}) on top of the
+// C ABI in include/zlb.h.  This file is the "stream driver": it does what baidu::zling::Encode/Decode do AROUND
+// the block pipeline (src/libzling.cpp:174-199,269-291 and :293-332,412-427) — pull bytes from the Inputter
+// until a 16 MiB block is full or the input ends, hand whole blocks to the GPU, push the framed result to the
+// Outputter, call the ActionHandler in the reference's order — and nothing of the codec itself.
+//
+// Ordering contract kept: every GetData/PutData/On* call is made from the calling thread; per
+// block the Outputter sees the sub-block records, the stop flag, and only then OnProcess(block) is invoked.
+// Batching: without an ActionHandler several blocks go to the GPU per call (unobservable); with one, encode still
+// batches (the handler only ever sees blocks after their bytes were emitted, in order) but decode proceeds one
+// block at a time because a handler may read from the Inputter inside OnProcess (demo/zling.cpp:124-132).
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/libzling/libzling.h"
+#include "../../include/zlb.h"
+
+namespace baidu {
+namespace zling {
+
+// ---- src/libzling_utils.cpp:40-95 ---------------------------------------------------------------------------
+int Inputter::GetChar() {
+    unsigned char c = 0;
+    GetData(&c, 1);
+    return c;
+}
+uint32_t Inputter::GetUInt32() {
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) v = (v << 8) | (uint32_t) GetChar();
+    return v;
+}
+int Outputter::PutChar(int v) {
+    unsigned char c = (unsigned char) v;
+    PutData(&c, 1);
+    return c;
+}
+uint32_t Outputter::PutUInt32(uint32_t v) {
+    for (int shift = 24; shift >= 0; shift -= 8) PutChar((int) ((v >> shift) & 0xff));
+    return v;
+}
+
+size_t FileInputter::GetData(unsigned char* buf, size_t len) {
+    const size_t got = fread(buf, 1, len, m_fp);
+    m_total_read += got;
+    return got;
+}
+bool FileInputter::IsEnd() {
+    const int c = fgetc(m_fp);
+    return ungetc(c, m_fp) == EOF;      // peek, as the reference does (libzling_utils.cpp:72-74)
+}
+bool FileInputter::IsErr() { return ferror(m_fp) != 0; }
+size_t FileInputter::GetInputSize() { return m_total_read; }
+
+size_t FileOutputter::PutData(unsigned char* buf, size_t len) {
+    const size_t put = fwrite(buf, 1, len, m_fp);
+    m_total_write += put;
+    return put;
+}
+bool FileOutputter::IsErr() { return ferror(m_fp) != 0; }
+size_t FileOutputter::GetOutputSize() { return m_total_write; }
+
+// ---- process-wide GPU context ---------------------------------------------------------------------------------
+namespace {
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+struct Gpu {
+    zlb_ctx* ctx = nullptr;
+    unsigned char* pin_in = nullptr;     // page-locked staging: max_blocks * 16 MiB
+    unsigned char* pin_out = nullptr;    // page-locked staging: zlb_encode_bound of the above
+    size_t in_cap = 0, out_cap = 0;
+    int max_blocks = 0;
+    ~Gpu() {
+        zlb_host_free(pin_in); zlb_host_free(pin_out);
+        zlb_destroy(ctx);
+    }
+};
+
+Gpu& gpu() {
+    static Gpu g;      // one call at a time per process, like the reference's single-threaded use
+    if (!g.ctx) {
+        g.max_blocks = env_int("ZLING_B200_BLOCKS", 8);
+        g.ctx = zlb_create(env_int("ZLING_B200_DEVICE", 0), g.max_blocks);
+        if (!g.ctx) throw std::runtime_error(std::string("libzling (B200): ") + zlb_last_error());
+        g.in_cap = (size_t) g.max_blocks * ZLB_BLOCK_BYTES;
+        g.out_cap = zlb_encode_bound(g.in_cap);
+        g.pin_in = (unsigned char*) zlb_host_alloc(g.in_cap + 64);
+        g.pin_out = (unsigned char*) zlb_host_alloc(g.out_cap + 64);
+        if (!g.pin_in || !g.pin_out) throw std::bad_alloc();
+    }
+    return g;
+}
+
+struct EncoderGuard {
+    zlb_encoder* e;
+    explicit EncoderGuard(zlb_encoder* e_) : e(e_) {}
+    ~EncoderGuard() { zlb_encoder_end(e); }
+};
+struct DecoderGuard {
+    zlb_decoder* d;
+    explicit DecoderGuard(zlb_decoder* d_) : d(d_) {}
+    ~DecoderGuard() { zlb_decoder_end(d); }
+};
+
+[[noreturn]] void raise_zlb(int rc) {
+    if (rc == ZLB_E_NOMEM) throw std::bad_alloc();
+    throw std::runtime_error(zlb_last_error());
+}
+
+// push `len` bytes, retrying short writes (libzling.cpp:273-276); false on outputter error
+bool put_all(Outputter* out, unsigned char* p, size_t len) {
+    size_t off = 0;
+    while (!out->IsErr() && off < len) off += out->PutData(p + off, len - off);
+    return !out->IsErr();
+}
+
+}  // namespace
+
+// ---- src/libzling.cpp:174-291 -------------------------------------------------------------------------------
+int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handler, int level) {
+    if (level < 0 || level > 4) return -1;       // the reference never terminates here; see libzling.h
+    if (action_handler) {
+        action_handler->SetInputterOutputter(inputter, outputter, true);
+        action_handler->OnInit();
+    }
+    Gpu& g = gpu();
+    EncoderGuard enc(zlb_encoder_begin(g.ctx, level));
+    if (!enc.e) raise_zlb(ZLB_E_CUDA);
+
+    bool io_error = false;
+    while (!io_error && !inputter->IsEnd() && !inputter->IsErr()) {
+        // fill up to max_blocks blocks; every block except the stream's last is exactly 16 MiB (libzling.cpp:193-196)
+        size_t have = 0;
+        while (have < g.in_cap && !inputter->IsEnd() && !inputter->IsErr()) {
+            have += inputter->GetData(g.pin_in + have, g.in_cap - have);
+            if (inputter->IsErr()) { io_error = true; break; }
+        }
+        if (io_error || have == 0) break;
+        size_t produced = 0;
+        const int rc = zlb_encode_blocks(enc.e, g.pin_in, have, g.pin_out, g.out_cap, &produced);
+        if (rc != ZLB_OK) raise_zlb(rc);
+
+        // hand the frames to the outputter block by block so that OnProcess keeps its place in the order
+        size_t at = 0;
+        for (size_t boff = 0; boff < have && !io_error; boff += ZLB_BLOCK_BYTES) {
+            const size_t blen = have - boff < ZLB_BLOCK_BYTES ? have - boff : (size_t) ZLB_BLOCK_BYTES;
+            size_t end = at;                      // find this block's stop flag by walking its sub-block headers
+            while (g.pin_out[end] == 1) {
+                const unsigned char* h = g.pin_out + end + 9;
+                end += 13 + ((size_t) h[0] << 24 | (size_t) h[1] << 16 | (size_t) h[2] << 8 | (size_t) h[3]);
+            }
+            end += 1;
+            if (!put_all(outputter, g.pin_out + at, end - at)) { io_error = true; break; }
+            at = end;
+            if (action_handler) action_handler->OnProcess(g.pin_in + boff, blen);
+        }
+    }
+    if (action_handler) action_handler->OnDone();
+    return (inputter->IsErr() || outputter->IsErr()) ? -1 : 0;
+}
+
+// ---- src/libzling.cpp:293-427 -------------------------------------------------------------------------------
+int Decode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handler) {
+    if (action_handler) {
+        action_handler->SetInputterOutputter(inputter, outputter, false);
+        action_handler->OnInit();
+    }
+    Gpu& g = gpu();
+    DecoderGuard dec(zlb_decoder_begin(g.ctx));
+    if (!dec.d) raise_zlb(ZLB_E_CUDA);
+    const int batch = action_handler ? 1 : g.max_blocks;
+    unsigned char* comp = g.pin_out;             // compressed bytes are staged in the larger buffer
+    bool io_error = false;
+
+    while (!io_error && !inputter->IsEnd()) {
+        // read exactly up to the stop flag of `batch` blocks: never consume input past a block end, because a
+        // handler may read its own bytes (e.g. a checksum) from the inputter inside OnProcess
+        size_t have = 0;
+        int blocks = 0;
+        while (blocks < batch && !inputter->IsEnd()) {
+            bool closed = false;
+            while (!inputter->IsEnd()) {
+                const int flag = inputter->GetChar();
+                if (flag != 0 && flag != 1) throw std::runtime_error("baidu::zling::Decode(): invalid encflag.");   // :315-317
+                comp[have++] = (unsigned char) flag;
+                if (flag == 0) { closed = true; break; }
+                for (int i = 0; i < 12; i++) comp[have + i] = (unsigned char) inputter->GetChar();
+                if (inputter->IsErr()) { io_error = true; break; }
+                const unsigned char* h = comp + have;
+                const uint32_t rlen = (uint32_t) h[4] << 24 | (uint32_t) h[5] << 16 | (uint32_t) h[6] << 8 | h[7];
+                const uint32_t olen = (uint32_t) h[8] << 24 | (uint32_t) h[9] << 16 | (uint32_t) h[10] << 8 | h[11];
+                have += 12;
+                if (rlen > ZLB_SUBBLOCK_SYMBOLS || olen > ZLB_SUBBLOCK_BYTES)
+                    throw std::runtime_error("baidu::zling::Decode(): invalid block size.");                        // :326-328
+                if (have + olen + 16 > g.out_cap) throw std::runtime_error("baidu::zling::Decode(): invalid block size.");
+                size_t off = 0;
+                while (!inputter->IsEnd() && off < olen) {                                                          // :329-332
+                    off += inputter->GetData(comp + have + off, olen - off);
+                    if (inputter->IsErr()) { io_error = true; break; }
+                }
+                if (io_error) break;
+                if (off < olen) throw std::runtime_error("baidu::zling::Decode(): invalid huffman stream. (truncated)");
+                have += olen;
+            }
+            if (io_error) break;
+            if (!closed) comp[have++] = 0;       // input ended without a stop flag: the reference still emits the block
+            blocks++;
+        }
+        if (io_error || have == 0) break;
+        size_t used = 0, produced = 0;
+        const int rc = zlb_decode_blocks(dec.d, comp, have, &used, g.pin_in, g.in_cap, &produced);
+        if (rc != ZLB_OK) raise_zlb(rc);
+        // blocks come back concatenated; every block but the last of the stream decodes to 16 MiB, but lengths
+        // are taken from the frames, not assumed: the last sub-block's encpos is the block length
+        size_t cpos = 0, opos = 0;
+        for (int b = 0; b < blocks && !io_error; b++) {
+            size_t blen = 0;
+            while (comp[cpos] == 1) {
+                const unsigned char* h = comp + cpos + 1;
+                blen = (size_t) h[0] << 24 | (size_t) h[1] << 16 | (size_t) h[2] << 8 | h[3];
+                cpos += 13 + ((size_t) h[8] << 24 | (size_t) h[9] << 16 | (size_t) h[10] << 8 | (size_t) h[11]);
+            }
+            cpos += 1;
+            if (!put_all(outputter, g.pin_in + opos, blen)) { io_error = true; break; }                             // :412-415
+            if (action_handler) action_handler->OnProcess(g.pin_in + opos, blen);
+            opos += blen;
+        }
+    }
+    if (action_handler) action_handler->OnDone();
+    return (inputter->IsErr() || outputter->IsErr()) ? -1 : 0;
+}
+
+}  // namespace zling
+}  // namespace baidu

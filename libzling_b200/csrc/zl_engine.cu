@@ -1,0 +1,534 @@
+// Host engine + C ABI (include/zlb.h) of the zling block pipeline.  One zlb_ctx per (process, GPU): device
+// buffers for up to max_blocks 16 MiB blocks, one CUDA stream, pinned mirrors of the small tables.
+//
+// Encode of one call (N blocks of one stream):
+//   H2D input -> [reset buckets -> zl_rolz_parse (one chain per block, all blocks concurrently)
+//                 -> zl_mtf_rank (stream order, carried state) -> zl_huff_build (per sub-block)]*
+//             -> host verifies the level-feedback plan (src/libzling.cpp:261-266) and, if a prediction was wrong,
+//                re-parses the affected blocks (loop marked * above)
+//             -> zl_huff_pack (frames written at their final offsets) -> D2H
+// There is no CPU implementation of any stage in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "../../include/zlb.h"
+#include "zl_kernels.cuh"
+
+#include "zl_kernels.cu"      // single translation unit: kernels + engine
+
+using namespace zl;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); return ZLB_E_CUDA; } } while (0)
+
+enum { EV_START, EV_H2D, EV_PARSE0, EV_PARSE1, EV_MTF1, EV_BUILD1, EV_PACK0, EV_PACK1, EV_END, EV_COUNT };
+
+struct zlb_ctx {
+    int device = 0, max_blocks = 0;
+    cudaStream_t stream = nullptr;
+    // device
+    uint8_t*  d_in = nullptr;       // max_blocks * 16 MiB + pad (host-input path)
+    uint8_t*  d_out = nullptr;      // zlb_encode_bound(max_blocks * 16 MiB); decode: output blocks
+    uint64_t* d_ring = nullptr;
+    uint16_t* d_hash = nullptr;
+    uint32_t* d_tok = nullptr;      // encode: tokens; decode: u16 symbols (2 per u32)
+    uint32_t* d_lit = nullptr;
+    SubBlock* d_sub = nullptr;
+    HuffTables* d_tab = nullptr;
+    uint32_t *d_nsub = nullptr, *d_ntok = nullptr, *d_nlit = nullptr, *d_ilen = nullptr;
+    uint8_t  *d_plan = nullptr, *d_active = nullptr, *d_active2 = nullptr, *d_ckpt = nullptr;
+    unsigned long long* d_outoff = nullptr;
+    DecSub*   d_decsub = nullptr;
+    int*      d_status = nullptr;
+    uint32_t* d_decring = nullptr;
+    uint8_t*  d_comp = nullptr;     // decode: compressed input
+    size_t    comp_cap = 0, out_cap = 0, decsub_cap = 0;
+    // pinned host mirrors
+    SubBlock* h_sub = nullptr;
+    uint32_t *h_nsub = nullptr, *h_ntok = nullptr, *h_nlit = nullptr, *h_ilen = nullptr;
+    uint8_t  *h_plan = nullptr, *h_active = nullptr, *h_active2 = nullptr;
+    unsigned long long* h_outoff = nullptr;
+    int*      h_status = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    zlb_stats stats = {};
+    int last_nblocks = 0;
+};
+
+struct zlb_encoder {
+    zlb_ctx* ctx;
+    int level, cur_level;
+    uint8_t* d_state[2];     // MTF rank->byte tables, ping-pong (input of a call stays intact until it succeeds)
+    int cur;
+};
+struct zlb_decoder {
+    zlb_ctx* ctx;
+    uint8_t* d_state;
+};
+
+static size_t bound_bytes(size_t n) {
+    // per sub-block: 13 frame bytes + 273 table bytes + <= 15 bits/symbol for <= 262144 symbols; a sub-block
+    // covers >= 262143 input bytes except the last of each block; + 1 stop byte per block
+    const size_t blocks = n / ZLB_BLOCK_BYTES + 1;
+    const size_t subs = n / 262143 + blocks + 1;
+    return n + n / 64 + subs * (13 + 273 + 8) + blocks + 1024;
+}
+
+extern "C" {
+
+const char* zlb_last_error(void) { return g_err; }
+const char* zlb_version(void) { return "libzling_b200 0.1 (sm_100a)"; }
+size_t zlb_encode_bound(size_t n) { return bound_bytes(n); }
+
+void* zlb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fail(ZLB_E_NOMEM, "zlb_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+void zlb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int zlb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void zlb_destroy(zlb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* dev[] = { c->d_in, c->d_out, c->d_ring, c->d_hash, c->d_tok, c->d_lit, c->d_sub, c->d_tab, c->d_nsub, c->d_ntok, c->d_nlit,
+                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp };
+    for (void* p : dev) if (p) cudaFree(p);
+    void* host[] = { c->h_sub, c->h_nsub, c->h_ntok, c->h_nlit, c->h_ilen, c->h_plan, c->h_active, c->h_active2, c->h_outoff, c->h_status };
+    for (void* p : host) if (p) cudaFreeHost(p);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int ctx_alloc(zlb_ctx* c) {
+    const size_t nb = (size_t) c->max_blocks, nsb = nb * kMaxSubPerBlock;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e : c->ev) CU(cudaEventCreate(&e));
+    c->out_cap = bound_bytes(nb * kBlockBytes);
+    c->comp_cap = c->out_cap;
+    c->decsub_cap = nb * 160;       // >= 65 sub-blocks per block in valid streams; more are accepted up to this
+    CU(cudaMalloc(&c->d_in, nb * kBlockBytes + 256));
+    CU(cudaMalloc(&c->d_out, c->out_cap + 256));
+    CU(cudaMalloc(&c->d_ring, nb * kRingStride * sizeof(uint64_t)));
+    CU(cudaMalloc(&c->d_hash, nb * kHashStride * sizeof(uint16_t)));
+    CU(cudaMalloc(&c->d_tok, nb * kTokStride * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_lit, nb * kLitStride * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_sub, nsb * sizeof(SubBlock)));
+    CU(cudaMalloc(&c->d_tab, nsb * sizeof(HuffTables)));
+    CU(cudaMalloc(&c->d_nsub, nb * 4)); CU(cudaMalloc(&c->d_ntok, nb * 4)); CU(cudaMalloc(&c->d_nlit, nb * 4)); CU(cudaMalloc(&c->d_ilen, nb * 4));
+    CU(cudaMalloc(&c->d_plan, nsb)); CU(cudaMalloc(&c->d_active, nb)); CU(cudaMalloc(&c->d_active2, nb)); CU(cudaMalloc(&c->d_ckpt, (nb + 1) * 65536));
+    CU(cudaMalloc(&c->d_outoff, nsb * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->d_decsub, c->decsub_cap * sizeof(DecSub)));
+    CU(cudaMalloc(&c->d_status, (c->decsub_cap + 4) * sizeof(int)));
+    CU(cudaMalloc(&c->d_decring, (size_t) 256 * kRing * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_comp, c->comp_cap + 256));
+    CU(cudaMemset(c->d_in, 0, nb * kBlockBytes + 256));
+    CU(cudaHostAlloc(&c->h_sub, nsb * sizeof(SubBlock), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_nsub, nb * 4, cudaHostAllocDefault)); CU(cudaHostAlloc(&c->h_ntok, nb * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_nlit, nb * 4, cudaHostAllocDefault)); CU(cudaHostAlloc(&c->h_ilen, nb * 4, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_plan, nsb, cudaHostAllocDefault)); CU(cudaHostAlloc(&c->h_active, nb, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_active2, nb, cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_outoff, nsb * sizeof(unsigned long long), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + 4) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaFuncSetAttribute(zl_mtf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+    CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+    return ZLB_OK;
+}
+
+zlb_ctx* zlb_create(int device, int max_blocks) {
+    if (max_blocks < 1 || max_blocks > 1024) { fail(ZLB_E_ARG, "zlb_create: max_blocks must be in 1..1024"); return nullptr; }
+    int n = zlb_device_count();
+    if (n <= 0) { fail(ZLB_E_NODEVICE, "zlb_create: no CUDA device available (this library has no CPU path)"); return nullptr; }
+    if (device < 0 || device >= n) { fail(ZLB_E_ARG, "zlb_create: device index out of range"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { fail(ZLB_E_CUDA, "zlb_create: cudaSetDevice failed"); return nullptr; }
+    zlb_ctx* c = new (std::nothrow) zlb_ctx();
+    if (!c) { fail(ZLB_E_NOMEM, "zlb_create: out of host memory"); return nullptr; }
+    c->device = device; c->max_blocks = max_blocks;
+    if (ctx_alloc(c) != ZLB_OK) { zlb_destroy(c); return nullptr; }
+    return c;
+}
+int zlb_max_blocks(const zlb_ctx* c) { return c ? c->max_blocks : ZLB_E_ARG; }
+
+int zlb_get_stats(const zlb_ctx* c, zlb_stats* out) {
+    if (!c || !out) return fail(ZLB_E_ARG, "zlb_get_stats: null argument");
+    *out = c->stats;
+    return ZLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ encoder
+zlb_encoder* zlb_encoder_begin(zlb_ctx* c, int level) {
+    if (!c) { fail(ZLB_E_ARG, "zlb_encoder_begin: null context"); return nullptr; }
+    if (level < 0 || level > 4) { fail(ZLB_E_ARG, "zlb_encoder_begin: level must be 0..4"); return nullptr; }   // lz.cpp:136
+    cudaSetDevice(c->device);
+    zlb_encoder* e = new (std::nothrow) zlb_encoder();
+    if (!e) { fail(ZLB_E_NOMEM, "zlb_encoder_begin: out of host memory"); return nullptr; }
+    e->ctx = c; e->level = level; e->cur_level = level; e->cur = 0; e->d_state[0] = e->d_state[1] = nullptr;
+    uint8_t init[65536];
+    for (int ctx = 0; ctx < 256; ctx++) memcpy(init + ctx * 256, kMtfInit, 256);          // lz.cpp:106-111
+    if (cudaMalloc(&e->d_state[0], 65536) != cudaSuccess || cudaMalloc(&e->d_state[1], 65536) != cudaSuccess ||
+        cudaMemcpy(e->d_state[0], init, 65536, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(ZLB_E_CUDA, "zlb_encoder_begin: device allocation failed");
+        if (e->d_state[0]) cudaFree(e->d_state[0]);
+        if (e->d_state[1]) cudaFree(e->d_state[1]);
+        delete e; return nullptr;
+    }
+    return e;
+}
+void zlb_encoder_end(zlb_encoder* e) {
+    if (!e) return;
+    cudaSetDevice(e->ctx->device);
+    cudaFree(e->d_state[0]); cudaFree(e->d_state[1]);
+    delete e;
+}
+int zlb_encoder_get_state(zlb_encoder* e, uint8_t* state) {
+    if (!e || !state) return fail(ZLB_E_ARG, "zlb_encoder_get_state: null argument");
+    CU(cudaSetDevice(e->ctx->device));
+    CU(cudaMemcpy(state, e->d_state[e->cur], 65536, cudaMemcpyDeviceToHost));
+    const int32_t lv = e->cur_level; memcpy(state + 65536, &lv, 4);
+    return ZLB_OK;
+}
+int zlb_encoder_set_state(zlb_encoder* e, const uint8_t* state) {
+    if (!e || !state) return fail(ZLB_E_ARG, "zlb_encoder_set_state: null argument");
+    int32_t lv; memcpy(&lv, state + 65536, 4);
+    if (lv < 0 || lv > 4) return fail(ZLB_E_ARG, "zlb_encoder_set_state: bad level");
+    CU(cudaSetDevice(e->ctx->device));
+    CU(cudaMemcpy(e->d_state[e->cur], state, 65536, cudaMemcpyHostToDevice));
+    e->cur_level = lv;
+    return ZLB_OK;
+}
+
+// the level-feedback rule: 1.0 * olen / (consumed + 1) > 0.95, libzling.cpp:261 (exact in integers: SURVEY §8 a11)
+static inline bool incompressible(const SubBlock& s) {
+    return (unsigned long long) s.olen * 20ull > (unsigned long long) (s.enc_end - s.enc_begin + 1) * 19ull;
+}
+
+static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after) {
+    zlb_ctx* c = e->ctx;
+    cudaStream_t st = c->stream;
+    const int nb = (int) ((n + kBlockBytes - 1) / kBlockBytes);
+    c->last_nblocks = nb;
+    uint32_t launches = 0, parse_launches = 0, reparsed = 0;
+    for (int b = 0; b < nb; b++) {
+        c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
+        c->h_active[b] = 1;
+        memset(c->h_plan + (size_t) b * kMaxSubPerBlock, e->level, kMaxSubPerBlock);
+    }
+    c->h_plan[0] = (uint8_t) e->cur_level;                        // current_level outlives blocks, libzling.cpp:185
+    CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
+
+    uint8_t* state_in = e->d_state[e->cur];
+    uint8_t* state_out = e->d_state[e->cur ^ 1];
+    ParseArgs pa;
+    pa.in = d_in; pa.ilen = c->d_ilen; pa.plan = c->d_plan; pa.active = c->d_active; pa.ring = c->d_ring; pa.hash = c->d_hash;
+    pa.tok = c->d_tok; pa.lit = c->d_lit; pa.sub = c->d_sub; pa.nsub = c->d_nsub; pa.ntok = c->d_ntok; pa.nlit = c->d_nlit;
+
+    int first_dirty = 0, final_level = e->cur_level;
+    float ms_parse = 0, ms_mtf = 0, ms_build = 0;
+    for (int pass = 0;; pass++) {
+        CU(cudaMemcpyAsync(c->d_plan, c->h_plan, (size_t) nb * kMaxSubPerBlock, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev[EV_PARSE0], st));
+        zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
+        zl_rolz_parse_kernel<<<nb, 32, 0, st>>>(pa);
+        CU(cudaEventRecord(c->ev[EV_PARSE1], st));
+        zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
+        CU(cudaEventRecord(c->ev[EV_MTF1], st));
+        // everything from the first re-parsed block on has new MTF ranks: rebuild those tables
+        for (int b = 0; b < nb; b++) c->h_active2[b] = b >= first_dirty;
+        CU(cudaMemcpyAsync(c->d_active2, c->h_active2, nb, cudaMemcpyHostToDevice, st));
+        zl_huff_build_kernel<<<dim3(kMaxSubPerBlock, nb), 256, 0, st>>>(c->d_tok, c->d_sub, c->d_nsub, c->d_active2, c->d_tab);
+        CU(cudaEventRecord(c->ev[EV_BUILD1], st));
+        CU(cudaMemcpyAsync(c->h_sub, c->d_sub, (size_t) nb * kMaxSubPerBlock * sizeof(SubBlock), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_nsub, c->d_nsub, nb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(c->h_ntok, c->d_ntok, nb * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaGetLastError());
+        launches += 4; parse_launches += 1;
+        { float t; cudaEventElapsedTime(&t, c->ev[EV_PARSE0], c->ev[EV_PARSE1]); ms_parse += t;
+          cudaEventElapsedTime(&t, c->ev[EV_PARSE1], c->ev[EV_MTF1]); ms_mtf += t;
+          cudaEventElapsedTime(&t, c->ev[EV_MTF1], c->ev[EV_BUILD1]); ms_build += t; }
+
+        // verify the plan in stream order (libzling.cpp:261-266)
+        int cur = e->cur_level, bad_b = -1, bad_j = -1;
+        for (int b = 0; b < nb && bad_b < 0; b++) {
+            const int ns = (int) c->h_nsub[b];
+            if (ns > kMaxSubPerBlock) return fail(ZLB_E_CUDA, "internal: sub-block table overflow");
+            for (int j = 0; j < ns; j++) {
+                const SubBlock& s = c->h_sub[(size_t) b * kMaxSubPerBlock + j];
+                if ((int) s.level != cur) { bad_b = b; bad_j = j; break; }
+                cur = incompressible(s) ? 0 : e->level;
+            }
+        }
+        if (bad_b < 0) { final_level = cur; break; }
+        if (pass > nb * kMaxSubPerBlock + 4) return fail(ZLB_E_CUDA, "internal: level-feedback replay did not converge");
+        // Re-plan block bad_b: sub-blocks before bad_j are verified; bad_j gets the level the reference would
+        // use; later ones are predicted from how compressible the same index was in the wrong run (incompressible
+        // data stays incompressible at any level).  A wrong guess only costs another pass, never correctness.
+        uint8_t* plan = c->h_plan + (size_t) bad_b * kMaxSubPerBlock;
+        const int ns = (int) c->h_nsub[bad_b];
+        plan[bad_j] = (uint8_t) cur;
+        for (int j = bad_j + 1; j < kMaxSubPerBlock; j++) {
+            const bool prev_bad = j - 1 < ns && incompressible(c->h_sub[(size_t) bad_b * kMaxSubPerBlock + j - 1]);
+            plan[j] = prev_bad ? 0 : (uint8_t) e->level;
+        }
+        // first sub-block of the next block follows the last sub-block of this one (prediction)
+        if (bad_b + 1 < nb && ns > 0) {
+            const bool last_bad = incompressible(c->h_sub[(size_t) bad_b * kMaxSubPerBlock + ns - 1]);
+            const uint8_t want = last_bad ? 0 : (uint8_t) e->level;
+            uint8_t* nplan = c->h_plan + (size_t) (bad_b + 1) * kMaxSubPerBlock;
+            for (int b = 0; b < nb; b++) c->h_active[b] = 0;
+            if (nplan[0] != want) { nplan[0] = want; c->h_active[bad_b + 1] = 1; reparsed++; }
+        } else {
+            for (int b = 0; b < nb; b++) c->h_active[b] = 0;
+        }
+        c->h_active[bad_b] = 1; reparsed++;
+        first_dirty = bad_b;
+    }
+
+    // layout of the framed stream: per sub-block 1 + 12 + olen bytes, one stop byte per block
+    unsigned long long off = 0, ntok = 0, nsub_total = 0;
+    for (int b = 0; b < nb; b++) {
+        for (int j = 0; j < (int) c->h_nsub[b]; j++) {
+            c->h_outoff[(size_t) b * kMaxSubPerBlock + j] = off;
+            off += 13ull + c->h_sub[(size_t) b * kMaxSubPerBlock + j].olen;
+        }
+        off += 1;
+        ntok += c->h_ntok[b]; nsub_total += c->h_nsub[b];
+    }
+    if (nb == 0) off = 0;
+    if (off > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_blocks: output buffer too small");
+    if (nb > 0) {
+        CU(cudaMemcpyAsync(c->d_outoff, c->h_outoff, (size_t) nb * kMaxSubPerBlock * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev[EV_PACK0], st));
+        zl_huff_pack_kernel<<<dim3(kMaxSubPerBlock, nb), 512, 0, st>>>(c->d_tok, c->d_sub, c->d_nsub, c->d_tab, c->d_outoff, d_out);
+        CU(cudaEventRecord(c->ev[EV_PACK1], st));
+        CU(cudaGetLastError());
+        launches += 1;
+    }
+    *out_len = (size_t) off;
+    *level_after = final_level;       // the caller commits (state ping-pong + level) once the call has succeeded
+    c->stats.ms_parse = ms_parse; c->stats.ms_mtf = ms_mtf; c->stats.ms_huff_build = ms_build;
+    c->stats.launches = launches; c->stats.parse_launches = parse_launches; c->stats.reparsed_blocks = reparsed;
+    c->stats.tokens = ntok; c->stats.subblocks = nsub_total;
+    return ZLB_OK;
+}
+
+static int check_encode_args(zlb_encoder* e, const void* in, size_t n, const void* out, size_t* out_len) {
+    if (!e || !out_len || (n && (!in || !out))) return fail(ZLB_E_ARG, "zlb_encode_blocks: null argument");
+    if (n > (size_t) e->ctx->max_blocks * kBlockBytes) return fail(ZLB_E_ARG, "zlb_encode_blocks: more than max_blocks blocks in one call");
+    return ZLB_OK;
+}
+
+static void finish_stats(zlb_ctx* c, bool with_pack) {
+    float t = 0;
+    c->stats.ms_pack = 0; c->stats.ms_total = 0; c->stats.ms_h2d = 0; c->stats.ms_d2h = 0;
+    if (with_pack && cudaEventElapsedTime(&t, c->ev[EV_PACK0], c->ev[EV_PACK1]) == cudaSuccess) c->stats.ms_pack = t;
+    if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[EV_END]) == cudaSuccess) c->stats.ms_total = t;
+    if (cudaEventElapsedTime(&t, c->ev[EV_START], c->ev[EV_H2D]) == cudaSuccess) c->stats.ms_h2d = t;
+    cudaGetLastError();
+}
+
+int zlb_encode_blocks_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len) {
+    int rc = check_encode_args(e, d_in, n, d_out, out_len);
+    if (rc) return rc;
+    zlb_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    *out_len = 0;
+    if (n == 0) return ZLB_OK;
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+    int level_after = e->cur_level;
+    rc = encode_device(e, d_in, n, d_out, out_cap, out_len, &level_after);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_END], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    finish_stats(c, true);
+    e->cur ^= 1; e->cur_level = level_after;
+    return ZLB_OK;
+}
+
+int zlb_encode_blocks(zlb_encoder* e, const uint8_t* in, size_t n, uint8_t* out, size_t out_cap, size_t* out_len) {
+    int rc = check_encode_args(e, in, n, out, out_len);
+    if (rc) return rc;
+    zlb_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    *out_len = 0;
+    if (n == 0) return ZLB_OK;                                    // empty input => empty stream (libzling.cpp:187)
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    CU(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_in + n, 0, 64, c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+    size_t produced = 0;
+    int level_after = e->cur_level;
+    rc = encode_device(e, c->d_in, n, c->d_out, c->out_cap, &produced, &level_after);
+    if (rc) return rc;
+    if (produced > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_blocks: output buffer too small");
+    CU(cudaMemcpyAsync(out, c->d_out, produced, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[EV_END], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    finish_stats(c, true);
+    { float t = 0; if (cudaEventElapsedTime(&t, c->ev[EV_PACK1], c->ev[EV_END]) == cudaSuccess) c->stats.ms_d2h = t; cudaGetLastError(); }
+    *out_len = produced;
+    e->cur ^= 1; e->cur_level = level_after;
+    return ZLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ debug / tests
+int zlb_debug_tokens(zlb_ctx* c, int blk, uint32_t* tok, size_t cap, size_t* ntok) {
+    if (!c || !ntok || blk < 0 || blk >= c->last_nblocks) return fail(ZLB_E_ARG, "zlb_debug_tokens: bad argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->h_ntok[blk];
+    *ntok = n;
+    if (tok) CU(cudaMemcpy(tok, c->d_tok + (size_t) blk * kTokStride, (n < cap ? n : cap) * 4, cudaMemcpyDeviceToHost));
+    return ZLB_OK;
+}
+int zlb_debug_subblocks(zlb_ctx* c, int blk, zlb_subblock* sub, size_t cap, size_t* nsub) {
+    if (!c || !nsub || blk < 0 || blk >= c->last_nblocks) return fail(ZLB_E_ARG, "zlb_debug_subblocks: bad argument");
+    static_assert(sizeof(zlb_subblock) == sizeof(SubBlock), "ABI mirror out of sync");
+    const size_t n = c->h_nsub[blk];
+    *nsub = n;
+    if (sub) memcpy(sub, c->h_sub + (size_t) blk * kMaxSubPerBlock, (n < cap ? n : cap) * sizeof(SubBlock));
+    return ZLB_OK;
+}
+int zlb_debug_huff_tables(zlb_ctx* c, const uint32_t* freq, int ntables, int nsym, int cap, uint8_t* len_out, uint16_t* code_out) {
+    if (!c || !freq || !len_out || !code_out || ntables < 1 || nsym < 1 || nsym > kSyms1 || cap < 1 || cap > 15)
+        return fail(ZLB_E_ARG, "zlb_debug_huff_tables: bad argument");
+    CU(cudaSetDevice(c->device));
+    uint32_t* d_f = nullptr; uint8_t* d_l = nullptr; uint16_t* d_c = nullptr;
+    const size_t cnt = (size_t) ntables * nsym;
+    CU(cudaMalloc(&d_f, cnt * 4)); CU(cudaMalloc(&d_l, cnt)); CU(cudaMalloc(&d_c, cnt * 2));
+    CU(cudaMemcpy(d_f, freq, cnt * 4, cudaMemcpyHostToDevice));
+    zl_huff_tables_only_kernel<<<ntables, 256, 0, c->stream>>>(d_f, nsym, cap, d_l, d_c);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(len_out, d_l, cnt, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(code_out, d_c, cnt * 2, cudaMemcpyDeviceToHost));
+    cudaFree(d_f); cudaFree(d_l); cudaFree(d_c);
+    return ZLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decoder
+zlb_decoder* zlb_decoder_begin(zlb_ctx* c) {
+    if (!c) { fail(ZLB_E_ARG, "zlb_decoder_begin: null context"); return nullptr; }
+    cudaSetDevice(c->device);
+    zlb_decoder* d = new (std::nothrow) zlb_decoder();
+    if (!d) { fail(ZLB_E_NOMEM, "zlb_decoder_begin: out of host memory"); return nullptr; }
+    d->ctx = c; d->d_state = nullptr;
+    uint8_t init[65536];
+    for (int ctx = 0; ctx < 256; ctx++) memcpy(init + ctx * 256, kMtfInit, 256);          // lz.cpp:119-121
+    if (cudaMalloc(&d->d_state, 65536) != cudaSuccess || cudaMemcpy(d->d_state, init, 65536, cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(ZLB_E_CUDA, "zlb_decoder_begin: device allocation failed");
+        if (d->d_state) cudaFree(d->d_state);
+        delete d; return nullptr;
+    }
+    return d;
+}
+void zlb_decoder_end(zlb_decoder* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    cudaFree(d->d_state);
+    delete d;
+}
+
+int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consumed, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!d || !consumed || !out_len || (n && !in)) return fail(ZLB_E_ARG, "zlb_decode_blocks: null argument");
+    zlb_ctx* c = d->ctx;
+    CU(cudaSetDevice(c->device));
+    *consumed = 0; *out_len = 0;
+    if (n == 0) return ZLB_OK;
+    // walk the container on the host (flag / BE32 x3 / payload, libzling.cpp:313-332)
+    std::vector<DecSub> subs;
+    size_t at = 0;
+    int nblocks = 0;
+    while (at < n && nblocks < c->max_blocks) {
+        uint32_t sym_off = 0;
+        size_t p = at;
+        bool closed = false;
+        const size_t first_sub = subs.size();
+        while (p < n) {
+            const int flag = in[p++];
+            if (flag != 0 && flag != 1) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid encflag.");   // :315-317
+            if (flag == 0) { closed = true; break; }
+            if (p + 12 > n) break;
+            auto be32 = [&](size_t q) { return (uint32_t) in[q] << 24 | (uint32_t) in[q + 1] << 16 | (uint32_t) in[q + 2] << 8 | (uint32_t) in[q + 3]; };
+            DecSub s;
+            s.encpos = be32(p); s.rlen = be32(p + 4); s.olen = be32(p + 8); p += 12;
+            if (s.rlen > (uint32_t) kSubSymbols || s.olen > (uint32_t) kSubBytesMax)
+                return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid block size.");                        // :326-328
+            if (s.olen < (uint32_t) kTableBytes || s.encpos > (uint32_t) kBlockBytes)
+                return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid block size.");
+            if (p + s.olen > n) { p = n + 1; break; }
+            s.payload_off = p; s.block = (uint32_t) nblocks; s.sym_off = sym_off; s.pad = 0;
+            if ((size_t) sym_off + s.rlen > 2 * kTokStride) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): lzdecode failed.");
+            sym_off += s.rlen;
+            p += s.olen;
+            subs.push_back(s);
+        }
+        if (!closed) { subs.resize(first_sub); break; }          // incomplete block: leave it for the next call
+        at = p; nblocks++;
+        if (subs.size() > c->decsub_cap) return fail(ZLB_E_FORMAT, "zlb_decode_blocks: too many sub-blocks in one call");
+    }
+    if (nblocks == 0) return fail(ZLB_E_ARG, "zlb_decode_blocks: input holds no complete block");
+    if (at > c->comp_cap) return fail(ZLB_E_ARG, "zlb_decode_blocks: compressed input larger than the context's buffer");
+    cudaStream_t st = c->stream;
+    const int ns = (int) subs.size();
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    CU(cudaMemcpyAsync(c->d_comp, in, at, cudaMemcpyHostToDevice, st));
+    if (ns) CU(cudaMemcpyAsync(c->d_decsub, subs.data(), (size_t) ns * sizeof(DecSub), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->d_status, 0, ((size_t) ns + 4) * sizeof(int), st));
+    CU(cudaMemsetAsync(c->d_nsub, 0, (size_t) nblocks * 4, st));
+    CU(cudaEventRecord(c->ev[EV_H2D], st));
+    uint16_t* d_sym = reinterpret_cast<uint16_t*>(c->d_tok);
+    if (ns) {
+        zl_huff_decode_kernel<<<ns, 256, 65536, st>>>(c->d_comp, c->d_decsub, d_sym, c->d_status);
+        zl_rolz_decode_kernel<<<1, 32, 65536, st>>>(c->d_decsub, ns, d_sym, c->d_in, c->d_decring, d->d_state, c->d_nsub, c->d_status + ns);
+    }
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, ((size_t) ns + 4) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_nsub, c->d_nsub, (size_t) nblocks * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (int i = 0; i < ns; i++) {
+        if (c->h_status[i] == 1) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid huffman stream. (bad code1)");   // :382
+        if (c->h_status[i] == 2) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid huffman stream. (bad code2)");   // :392
+        if (c->h_status[i] == 3) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid huffman stream. (bad ex-bits)"); // :399
+    }
+    if (c->h_status[ns] != 0) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): lzdecode failed.");                         // :407
+    size_t total = 0;
+    for (int b = 0; b < nblocks; b++) total += c->h_nsub[b];
+    if (total > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_decode_blocks: output buffer too small");
+    size_t w = 0;
+    for (int b = 0; b < nblocks; b++) {
+        if (c->h_nsub[b]) CU(cudaMemcpyAsync(out + w, c->d_in + (size_t) b * kBlockBytes, c->h_nsub[b], cudaMemcpyDeviceToHost, st));
+        w += c->h_nsub[b];
+    }
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    finish_stats(c, false);
+    c->stats.launches = ns ? 2 : 0; c->stats.subblocks = (uint64_t) ns;
+    *consumed = at; *out_len = total;
+    return ZLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+"""The C++ drop-in API (baidu::zling::Encode/Decode with File{In,Out}putter and an ActionHandler) on the GPU:
+a small program written against include/libzling/libzling.h, linked with libzling.so, must produce the oracle's
+bytes and round-trip.  (On the container with /root/reference, test_abi_cpu additionally links the reference's
+own CLI against this library.)"""
+import os
+import subprocess
+
+import pytest
+
+import libzling_b200
+from _inputs import small_cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cli(tmp_path_factory):
+    d = tmp_path_factory.mktemp("cxx")
+    exe = d / "zl_cli"
+    libdir = os.path.dirname(libzling_b200.lib_path())
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx", "zl_cli.cpp"),
+                           "-o", str(exe), "-L", libdir, "-lzling", "-Wl,-rpath," + libdir])
+    return str(exe), d
+
+
+def test_cxx_encode_decode(cli, oracle):
+    exe, d = cli
+    cases = dict(small_cases())
+    for name in ("empty", "one", "hello", "text1m", "text_random_text"):
+        data = cases[name]
+        src, z, back = d / "in.bin", d / "out.zl", d / "back.bin"
+        src.write_bytes(data)
+        for level in (0, 3):
+            r = subprocess.run([exe, "e%d" % level, str(src), str(z)], capture_output=True)
+            assert r.returncode == 0, r.stderr
+            assert z.read_bytes() == oracle.encode(data, level), (name, level)
+            # handler bookkeeping printed by the CLI: one OnProcess per 16 MiB block, after its bytes were written
+            assert b"blocks=%d" % ((len(data) + (1 << 24) - 1) >> 24) in r.stderr, r.stderr
+            r = subprocess.run([exe, "d", str(z), str(back)], capture_output=True)
+            assert r.returncode == 0, r.stderr
+            assert back.read_bytes() == data, (name, level)
+
+
+def test_cxx_decode_malformed_throws(cli, oracle):
+    exe, d = cli
+    z = bytearray(oracle.encode(b"hello " * 50, 0))
+    z[0] = 7
+    (d / "bad.zl").write_bytes(bytes(z))
+    r = subprocess.run([exe, "d", str(d / "bad.zl"), str(d / "bad.out")], capture_output=True)
+    assert r.returncode == 3 and b"invalid encflag" in r.stderr
