@@ -106,6 +106,13 @@ typedef struct {
     uint32_t reparsed_blocks; /* blocks parsed again because the level-feedback prediction was wrong */
     uint64_t tokens;          /* tokens produced by the last call */
     uint64_t subblocks;
+    uint64_t slow_main;       /* parse: probes redone exactly on the live structure (stale record) */
+    uint64_t slow_lazy;       /* parse: lazy probes redone exactly */
+    uint64_t window_hits;     /* parse: candidates served by the in-window mini dictionary */
+    uint64_t windows;         /* parse: speculate/resolve windows executed */
+    uint64_t cyc_spec;        /* parse: SM cycles spent in the speculate phase, summed over blocks */
+    uint64_t cyc_resolve;     /* parse: SM cycles spent in the resolve phase, summed over blocks */
+    uint64_t general_path;    /* parse: tokens resolved through the mini-dictionary path instead of the frozen decision */
 } zlb_stats;
 int zlb_get_stats(const zlb_ctx* ctx, zlb_stats* out);
 

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -61,6 +62,9 @@ struct zlb_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     zlb_stats stats = {};
     int last_nblocks = 0;
+    int parse_version = 2;          // ZLB_PARSE=1 selects the literal one-warp-per-block chain walker (exact fallback / A-B)
+    V2Counters* d_v2c = nullptr;
+    V2Counters  h_v2c = {};
 };
 
 struct zlb_encoder {
@@ -110,7 +114,7 @@ void zlb_destroy(zlb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* dev[] = { c->d_in, c->d_out, c->d_ring, c->d_hash, c->d_tok, c->d_lit, c->d_sub, c->d_tab, c->d_nsub, c->d_ntok, c->d_nlit,
-                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp };
+                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp, c->d_v2c };
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = { c->h_sub, c->h_nsub, c->h_ntok, c->h_nlit, c->h_ilen, c->h_plan, c->h_active, c->h_active2, c->h_outoff, c->h_status };
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -149,6 +153,9 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaHostAlloc(&c->h_active2, nb, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_outoff, nsb * sizeof(unsigned long long), cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + 4) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaMalloc(&c->d_v2c, sizeof(V2Counters)));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv == '1') c->parse_version = 1; }
     CU(cudaFuncSetAttribute(zl_mtf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
@@ -249,7 +256,15 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(c->ev[EV_PARSE0], st));
         zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
-        zl_rolz_parse_kernel<<<nb, 32, 0, st>>>(pa);
+        if (c->parse_version == 1) {
+            zl_rolz_parse_kernel<<<nb, 32, 0, st>>>(pa);
+        } else {
+            const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
+            const int W = e->level <= 2 ? 1024 : 512;
+            const V2Layout lay = v2_layout(W, dmax, lmax);
+            if (pass == 0) CU(cudaMemsetAsync(c->d_v2c, 0, sizeof(V2Counters), st));
+            zl_rolz_parse_v2_kernel<<<nb, kV2Threads, lay.total, st>>>(pa, W, dmax, lmax, e->level, c->d_v2c);
+        }
         CU(cudaEventRecord(c->ev[EV_PARSE1], st));
         zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
         CU(cudaEventRecord(c->ev[EV_MTF1], st));
@@ -330,6 +345,15 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
     c->stats.ms_parse = ms_parse; c->stats.ms_mtf = ms_mtf; c->stats.ms_huff_build = ms_build;
     c->stats.launches = launches; c->stats.parse_launches = parse_launches; c->stats.reparsed_blocks = reparsed;
     c->stats.tokens = ntok; c->stats.subblocks = nsub_total;
+    c->stats.slow_main = c->stats.slow_lazy = c->stats.window_hits = c->stats.windows = 0;
+    c->stats.cyc_spec = c->stats.cyc_resolve = c->stats.general_path = 0;
+    if (c->parse_version != 1) {
+        CU(cudaMemcpyAsync(&c->h_v2c, c->d_v2c, sizeof(V2Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        c->stats.slow_main = c->h_v2c.slow_main; c->stats.slow_lazy = c->h_v2c.slow_lazy;
+        c->stats.window_hits = c->h_v2c.md_hits; c->stats.windows = c->h_v2c.windows;
+        c->stats.cyc_spec = c->h_v2c.cyc_spec; c->stats.cyc_resolve = c->h_v2c.cyc_resolve; c->stats.general_path = c->h_v2c.general;
+    }
     return ZLB_OK;
 }
 

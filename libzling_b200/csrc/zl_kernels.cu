@@ -231,6 +231,10 @@ __global__ void __launch_bounds__(32) zl_rolz_parse_kernel(ParseArgs a) {
     if (lane == 0) { a.nsub[b] = j; a.ntok[b] = nt; a.nlit[b] = nl; }
 }
 
+}  // namespace zl
+#include "zl_parse_v2.cuh"
+namespace zl {
+
 // =====================================================================================================
 // MTF rank pass (stream order, state carried across blocks and calls)
 // =====================================================================================================
