@@ -62,9 +62,13 @@ struct zlb_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     zlb_stats stats = {};
     int last_nblocks = 0;
-    int parse_version = 2;          // ZLB_PARSE=1 selects the literal one-warp-per-block chain walker (exact fallback / A-B)
+    int parse_version = 3;          // ZLB_PARSE=1: literal one-warp-per-block chain walker, 2: windowed speculate/resolve, 3: pipelined (default)
+    int mtf_version = 2;            // ZLB_MTF=1: one warp per stream, 2: one CTA per context (default)
     V2Counters* d_v2c = nullptr;
     V2Counters  h_v2c = {};
+    V3Counters* d_v3c = nullptr;
+    V3Counters  h_v3c = {};
+    uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
 };
 
 struct zlb_encoder {
@@ -114,7 +118,8 @@ void zlb_destroy(zlb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* dev[] = { c->d_in, c->d_out, c->d_ring, c->d_hash, c->d_tok, c->d_lit, c->d_sub, c->d_tab, c->d_nsub, c->d_ntok, c->d_nlit,
-                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp, c->d_v2c };
+                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp, c->d_v2c,
+                    c->d_v3c, c->d_lbuf, c->d_lhist, c->d_ctxoff };
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = { c->h_sub, c->h_nsub, c->h_ntok, c->h_nlit, c->h_ilen, c->h_plan, c->h_active, c->h_active2, c->h_outoff, c->h_status };
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -154,8 +159,14 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaHostAlloc(&c->h_outoff, nsb * sizeof(unsigned long long), cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + 4) * sizeof(int), cudaHostAllocDefault));
     CU(cudaMalloc(&c->d_v2c, sizeof(V2Counters)));
+    CU(cudaMalloc(&c->d_v3c, sizeof(V3Counters)));
+    CU(cudaMalloc(&c->d_lbuf, nb * kLitStride * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_lhist, nb * (size_t) kLitUnitsMax * 256 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_ctxoff, nb * 257 * sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv == '1') c->parse_version = 1; }
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3_layout(depth_main(4), depth_lazy1(4)).total));
+    { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv >= '1' && *pv <= '3') c->parse_version = *pv - '0'; }
+    { const char* pv = getenv("ZLB_MTF"); if (pv && *pv >= '1' && *pv <= '2') c->mtf_version = *pv - '0'; }
     CU(cudaFuncSetAttribute(zl_mtf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
@@ -258,6 +269,11 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
         if (c->parse_version == 1) {
             zl_rolz_parse_kernel<<<nb, 32, 0, st>>>(pa);
+        } else if (c->parse_version == 3) {
+            const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
+            const V3Layout lay = v3_layout(dmax, lmax);
+            if (pass == 0) CU(cudaMemsetAsync(c->d_v3c, 0, sizeof(V3Counters), st));
+            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, c->d_v3c);
         } else {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const int W = e->level <= 2 ? 1024 : 512;
@@ -266,7 +282,16 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             zl_rolz_parse_v2_kernel<<<nb, kV2Threads, lay.total, st>>>(pa, W, dmax, lmax, e->level, c->d_v2c);
         }
         CU(cudaEventRecord(c->ev[EV_PARSE1], st));
-        zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
+        if (c->mtf_version == 1) {
+            zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
+        } else {
+            const dim3 lgrid(kLitUnitsMax / kLitWarps, nb - first_dirty);
+            zl_lit_count_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, c->d_lhist);
+            zl_lit_scan_kernel<<<nb - first_dirty, 256, 0, st>>>(c->d_nlit, first_dirty, c->d_lhist, c->d_ctxoff);
+            zl_lit_scatter_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, c->d_lhist, c->d_lbuf);
+            zl_mtf_ctx_kernel<<<256, 32, 0, st>>>(c->d_tok, c->d_lbuf, c->d_ctxoff, first_dirty, nb, state_in, state_out, c->d_ckpt);
+            launches += 3;
+        }
         CU(cudaEventRecord(c->ev[EV_MTF1], st));
         // everything from the first re-parsed block on has new MTF ranks: rebuild those tables
         for (int b = 0; b < nb; b++) c->h_active2[b] = b >= first_dirty;
@@ -347,7 +372,14 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
     c->stats.tokens = ntok; c->stats.subblocks = nsub_total;
     c->stats.slow_main = c->stats.slow_lazy = c->stats.window_hits = c->stats.windows = 0;
     c->stats.cyc_spec = c->stats.cyc_resolve = c->stats.general_path = 0;
-    if (c->parse_version != 1) {
+    c->stats.cyc_total = 0;
+    if (c->parse_version == 3) {
+        CU(cudaMemcpyAsync(&c->h_v3c, c->d_v3c, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        c->stats.slow_main = c->h_v3c.slow; c->stats.window_hits = c->h_v3c.linkwalk; c->stats.windows = c->h_v3c.windows;
+        c->stats.cyc_spec = c->h_v3c.cyc_spec; c->stats.cyc_resolve = c->h_v3c.cyc_resolve; c->stats.general_path = c->h_v3c.general;
+        c->stats.cyc_total = c->h_v3c.cyc_total;
+    } else if (c->parse_version == 2) {
         CU(cudaMemcpyAsync(&c->h_v2c, c->d_v2c, sizeof(V2Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->stats.slow_main = c->h_v2c.slow_main; c->stats.slow_lazy = c->h_v2c.slow_lazy;

@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(32) zl_rolz_parse_kernel(ParseArgs a) {
 
 }  // namespace zl
 #include "zl_parse_v2.cuh"
+#include "zl_parse_v3.cuh"
 namespace zl {
 
 // =====================================================================================================
@@ -302,6 +303,146 @@ __global__ void __launch_bounds__(32) zl_mtf_rank_kernel(uint32_t* tok_all, cons
         const uint4* src = reinterpret_cast<const uint4*>(s_sym);
         for (int i = lane; i < 65536 / 16; i += 32) dst[i] = src[i];
     }
+}
+
+// =====================================================================================================
+// MTF rank pass, context-parallel form (zl_lit_count / zl_lit_scan / zl_lit_scatter / zl_mtf_ctx)
+// =====================================================================================================
+// The 256 MTF tables are independent (ZlingMTFEncoder m_mtf[256], src/libzling_lz.h:105), so the stream-order pass
+// splits into 256 chains: literals are bucketed by context with a stable counting sort (order inside a context is
+// stream order), then one CTA per context walks its list.  The longest list (context 0x20 on text) is the
+// critical path; everything else runs beside it.
+constexpr int kLitUnit = 8192;                                    // literals per warp in the bucketing kernels
+constexpr int kLitUnitsMax = kBlockBytes / kLitUnit;              // 2048 units per block at most
+constexpr int kLitWarps = 8;
+
+// grid (ceil(units / kLitWarps), nblocks); hist[b][unit][256]
+__global__ void __launch_bounds__(kLitWarps * 32) zl_lit_count_kernel(const uint32_t* tok_all, const uint32_t* lit_all, const uint32_t* nlit,
+                                                                    int first_block, uint32_t* hist) {
+    const int b = blockIdx.y + first_block, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kLitWarps + warp;
+    const int n = (int) nlit[b];
+    __shared__ uint32_t s_h[kLitWarps][256];
+    if (unit * kLitUnit >= n) return;
+    for (int i = lane; i < 256; i += 32) s_h[warp][i] = 0;
+    __syncwarp();
+    const uint32_t* tok = tok_all + (size_t) b * kTokStride;
+    const uint32_t* lit = lit_all + (size_t) b * kLitStride;
+    const int lo = unit * kLitUnit, hi = min(lo + kLitUnit, n);
+    for (int i = lo + lane; i < hi; i += 32) atomicAdd(&s_h[warp][tok_aux(tok[lit[i]]) & 0xff], 1u);
+    __syncwarp();
+    uint32_t* out = hist + ((size_t) b * kLitUnitsMax + unit) * 256;
+    for (int i = lane; i < 256; i += 32) out[i] = s_h[warp][i];
+}
+
+// grid nblocks, 256 threads: hist[b][unit][ctx] -> start offset of (unit, ctx) inside the block's bucketed list;
+// ctx_off[b][ctx] (257 entries) = start of each context's list
+__global__ void __launch_bounds__(256) zl_lit_scan_kernel(const uint32_t* nlit, int first_block, uint32_t* hist, uint32_t* ctx_off) {
+    const int b = blockIdx.x + first_block, ctx = threadIdx.x;
+    const int n = (int) nlit[b];
+    const int units = (n + kLitUnit - 1) / kLitUnit;
+    uint32_t* h = hist + (size_t) b * kLitUnitsMax * 256;
+    uint32_t total = 0;
+    for (int u = 0; u < units; u++) total += h[(size_t) u * 256 + ctx];
+    __shared__ uint32_t s_scan[256];
+    s_scan[ctx] = total;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        const uint32_t v = ctx >= d ? s_scan[ctx - d] : 0;
+        __syncthreads();
+        s_scan[ctx] += v;
+        __syncthreads();
+    }
+    uint32_t run = s_scan[ctx] - total;
+    ctx_off[(size_t) b * 257 + ctx] = run;
+    if (ctx == 255) ctx_off[(size_t) b * 257 + 256] = s_scan[255];
+    for (int u = 0; u < units; u++) { const uint32_t v = h[(size_t) u * 256 + ctx]; h[(size_t) u * 256 + ctx] = run; run += v; }
+}
+
+// same grid as the count kernel; lbuf[b][k] = token index << 8 | literal byte, grouped by context, stream order inside
+__global__ void __launch_bounds__(kLitWarps * 32) zl_lit_scatter_kernel(const uint32_t* tok_all, const uint32_t* lit_all, const uint32_t* nlit,
+                                                                      int first_block, const uint32_t* hist, uint32_t* lbuf_all) {
+    const int b = blockIdx.y + first_block, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kLitWarps + warp;
+    const int n = (int) nlit[b];
+    __shared__ uint32_t s_at[kLitWarps][256];
+    if (unit * kLitUnit >= n) return;
+    const uint32_t* base = hist + ((size_t) b * kLitUnitsMax + unit) * 256;
+    for (int i = lane; i < 256; i += 32) s_at[warp][i] = base[i];
+    __syncwarp();
+    const uint32_t* tok = tok_all + (size_t) b * kTokStride;
+    const uint32_t* lit = lit_all + (size_t) b * kLitStride;
+    uint32_t* lbuf = lbuf_all + (size_t) b * kLitStride;
+    const int lo = unit * kLitUnit, hi = min(lo + kLitUnit, n);
+    for (int i0 = lo; i0 < hi; i0 += 32) {
+        const int i = i0 + lane;
+        const bool live = i < hi;
+        uint32_t ti = 0, t = 0;
+        if (live) { ti = lit[i]; t = tok[ti]; }
+        const int ctx = live ? (int) (tok_aux(t) & 0xff) : 256 + lane;
+        const uint32_t same = __match_any_sync(0xffffffffu, ctx);
+        const int order = __popc(same & ((1u << lane) - 1u));
+        uint32_t at = 0;
+        if (live) at = s_at[warp][ctx] + order;
+        __syncwarp();
+        if (live && (same >> lane) == 1u) s_at[warp][ctx] = at + 1;       // last lane of the group advances the cursor
+        if (live) lbuf[at] = (ti << 8) | tok_byte(t);
+        __syncwarp();
+    }
+}
+
+constexpr int kMtfChunk = 256;                                    // literal records staged per round
+
+// grid 256 (one CTA = one warp per context).  Lane 0 walks the context's literal list of every block in stream
+// order (ZlingMTFEncoder::Encode, lz.cpp:112-117); all lanes prefetch the next records into shared memory.
+__global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const uint32_t* lbuf_all, const uint32_t* ctx_off, int first_block, int nblocks,
+                                                        const uint8_t* state_in, uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
+    const int ctx = blockIdx.x, lane = threadIdx.x;
+    __shared__ __align__(16) uint8_t s_sym[256];          // rank -> byte
+    __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
+    __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
+    {
+        const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
+        for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) s_rank[s_sym[i]] = (uint8_t) i;
+        __syncwarp();
+    }
+    for (int b = first_block; b < nblocks; b++) {
+        {   // MTF state at the start of block b (replay point for level-feedback re-parses)
+            uint8_t* dst = checkpoints + (size_t) b * 65536 + ctx * 256;
+            for (int i = lane; i < 256; i += 32) dst[i] = s_sym[i];
+        }
+        const uint32_t lo = ctx_off[(size_t) b * 257 + ctx], hi = ctx_off[(size_t) b * 257 + ctx + 1];
+        const uint32_t* list = lbuf_all + (size_t) b * kLitStride + lo;
+        const int n = (int) (hi - lo);
+        uint32_t* tok = tok_all + (size_t) b * kTokStride;
+        uint32_t pre[kMtfChunk / 32];
+        #pragma unroll
+        for (int q = 0; q < kMtfChunk / 32; q++) { const int i = q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
+        for (int base = 0, buf = 0; base < n; base += kMtfChunk, buf ^= 1) {
+            #pragma unroll
+            for (int q = 0; q < kMtfChunk / 32; q++) s_rec[buf][q * 32 + lane] = pre[q];
+            #pragma unroll
+            for (int q = 0; q < kMtfChunk / 32; q++) { const int i = base + kMtfChunk + q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
+            __syncwarp();
+            if (lane == 0) {
+                const int cnt = min(kMtfChunk, n - base);
+                for (int q = 0; q < cnt; q++) {
+                    const uint32_t rec = s_rec[buf][q];
+                    const uint32_t byte = rec & 0xffu;
+                    const int i = s_rank[byte], jn = mtf_next(i);
+                    const uint32_t other = s_sym[jn];
+                    s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;
+                    s_rank[other] = (uint8_t) i; s_rank[byte] = (uint8_t) jn;
+                    tok[rec >> 8] = (uint32_t) i | ((uint32_t) ctx << 10) | (byte << 22);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < 256; i += 32) state_out[ctx * 256 + i] = s_sym[i];
 }
 
 // =====================================================================================================

@@ -27,7 +27,7 @@
 
 namespace zl {
 
-constexpr int kV3Prod    = 512;                 // producer threads (16 warps)
+constexpr int kV3Prod    = 480;                 // producer threads (15 warps; 16 warps per CTA keep 128 registers per thread)
 constexpr int kV3Threads = kV3Prod + 32;        // + the resolver warp (warp 0)
 constexpr int kV3W       = kV3Prod - 2;         // main positions per window; each table also holds 2 lazy look-ahead positions
 constexpr int kV3R       = 2048;                // per-position ring (bytes, keys, links, insert marks): >= 3 W + 320
@@ -142,20 +142,23 @@ struct V3Ctx {
     uint32_t* rbw;                              // input bytes, ring of kV3R bytes viewed as words
     uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* ins; uint16_t* suf;
     uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru;
-    V3Table tab[2];
+    uint8_t* tab0; int tab_stride, t_hdr, t_node, t_eq, t_dec;   // two tables, selected arithmetically (no dynamic struct indexing)
     int dmax, lmax;
 };
+ZL_HD V3Table v3_table(const V3Ctx& c, int j) {
+    uint8_t* b = c.tab0 + (j & 1) * c.tab_stride;
+    V3Table t;
+    t.hdr = (uint32_t*) (b + c.t_hdr); t.node = (uint32_t*) (b + c.t_node); t.eq = (uint32_t*) (b + c.t_eq); t.dec = (uint2*) (b + c.t_dec);
+    return t;
+}
 
 __host__ __device__ inline void v3_bind(V3Ctx& c, uint8_t* smem, const V3Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
     c.blink = (uint16_t*) (smem + L.blink); c.ins = (uint16_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf);
     c.last = (uint32_t*) (smem + L.last); c.cnt = (uint32_t*) (smem + L.cnt); c.snap = (uint32_t*) (smem + L.snap);
     c.mru = (uint32_t*) (smem + L.mru);
-    for (int t = 0; t < 2; t++) {
-        uint8_t* b = smem + L.tab[t];
-        c.tab[t].hdr = (uint32_t*) (b + L.t_hdr); c.tab[t].node = (uint32_t*) (b + L.t_node);
-        c.tab[t].eq = (uint32_t*) (b + L.t_eq); c.tab[t].dec = (uint2*) (b + L.t_dec);
-    }
+    c.tab0 = smem + L.tab[0]; c.tab_stride = L.tab[1] - L.tab[0];
+    c.t_hdr = L.t_hdr; c.t_node = L.t_node; c.t_eq = L.t_eq; c.t_dec = L.t_dec;
     c.dmax = L.dmax; c.lmax = L.lmax;
 }
 
@@ -294,7 +297,7 @@ ZL_HD int v3_len_from_eq(const uint8_t* in, uint32_t x, uint32_t q, const uint32
     return v3_common_len_global(in, x, q, 132);
 }
 ZL_HD void v3_spec_position(const V3Ctx& c, int j, int rel) {
-    const V3Table& t = c.tab[j & 1];
+    const V3Table t = v3_table(c, j);
     const int x = j * kV3W + rel;
     const uint32_t k = c.key[x & (kV3R - 1)];
     if (k & kKeyInvalid) { t.hdr[rel] = (uint32_t) (kRing - 1) << 5; return; }
@@ -335,7 +338,7 @@ ZL_HD bool v3_eq_hit(const uint32_t* eqw, uint32_t at) {                 // byte
     return (z3_funnel(eqw[at >> 5], eqw[(at >> 5) + 1], at & 31u) & 0xfu) == 0xfu;
 }
 ZL_HD void v3_decide_position(const V3Ctx& c, int j, int rel, int level) {
-    const V3Table& t = c.tab[j & 1];
+    const V3Table t = v3_table(c, j);
     const int x = j * kV3W + rel;
     const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
     const uint32_t hdr = t.hdr[rel];
@@ -417,6 +420,9 @@ ZL_HD bool v3_link_hazard(const V3Ctx& c, int z, int base, int self) {
 struct V3Live { const V3Ctx* c; int k; int upto; };      // pending = starts in [k W, upto]
 ZL_HD uint64_t v3_live_entry(const V3Live& lv, uint32_t ctx, uint32_t n) {
     const V3Ctx& c = *lv.c;
+    const uint32_t done_k = c.snap[256 * (lv.k % 3) + ctx];              // inserts into ctx before window k (all in G)
+    const uint32_t ord = (n - done_k) & (kRing - 1);                     // n is pending iff it is insert number 1..pend of this window
+    if (ord == 0 || ord > c.cnt[ctx] - done_k) return z3_ld_ring(c.ring + (size_t) ctx * kRing + n);
     for (int y = lv.upto; y >= lv.k * kV3W; y--) {          // newest first; a ring slot is written at most once per window
         const uint32_t m = c.ins[y & (kV3R - 1)];
         if ((m & kInsStart) && (m & (kRing - 1)) == n && ((c.key[y & (kV3R - 1)] >> 13) & 0xffu) == ctx)
@@ -486,9 +492,19 @@ ZL_HD void v3_close_subblock(const V3Ctx& c, V3Run& r) {
     }
 }
 
+// Leading nodes of a record whose ring slots have not been overwritten after `kc` further inserts into the context.
+// A record node that HAS been overwritten ends the reference's walk right there when it is not the first one (the
+// slot now holds a newer, i.e. larger, position: the "offset <= next offset" test of lz.cpp:264 fires), so a record
+// cut at its first overwritten node is still exact; only an overwritten FIRST node needs the literal replay.
+ZL_HD int v3_valid_nodes(const V3Table& t, int rel, int dmax, int nvis, uint32_t head_b, uint32_t kc) {
+    int i = 0;
+    while (i < nvis && v3_ring_dist(t.node[rel * dmax + i] >> 9, head_b) > kc) i++;
+    return i;
+}
+
 // probe + insert at token start x of window k (MatchAndUpdate); returns the match length (0 = none) and *midx
 ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t* midx) {
-    const V3Table& t = c.tab[k & 1];
+    const V3Table t = v3_table(c, k);
     const int rel = x - k * kV3W;
     const int base = v3_base(k);
     const uint32_t* snap_b = c.snap + 256 * ((k + 2) % 3);               // counters at base(k)
@@ -500,19 +516,23 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
 
     const uint32_t cntc = c.cnt[ctx] + 1u, head = cntc & (kRing - 1);
     bool general = level != tlevel;
-    bool stale0 = false;
+    const uint32_t kc0 = cntc - snap_b[ctx];
     if (d.y & (kF_SELF | kF_L1 | kF_L2 | kF_ST0 | kF_ST1 | kF_ST2)) {
         const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (L2 > 0 ? 2 : 1) : 0;
         if (d.y & (kF_SELF | kF_L1 | kF_L2)) r.n_linkwalk++;
         if ((d.y & kF_SELF) && v3_link_hazard(c, x, base, -1)) general = true;
         if (nlazy >= 1 && (d.y & kF_L1) && v3_link_hazard(c, x + 1, base, x)) general = true;
         if (nlazy >= 2 && (d.y & kF_L2) && v3_link_hazard(c, x + 2, base, x)) general = true;
-        if (d.y & kF_ST0) { stale0 = (t.hdr[rel] >> 5) + 1u <= cntc - snap_b[ctx]; general |= stale0; }
+        if (d.y & kF_ST0) {
+            const uint32_t h0 = t.hdr[rel];
+            if ((h0 >> 5) + 1u <= kc0 && v3_valid_nodes(t, rel, c.dmax, (int) (h0 & 31u), snap_b[ctx] & (kRing - 1), kc0) < (int) (h0 & 31u)) general = true;
+        }
         for (int w = 1; w <= nlazy; w++) {
             if (d.y & (w == 1 ? kF_ST1 : kF_ST2)) {
                 const uint32_t cw = v3_rb8(c.rbw, (uint32_t) (x + w - 1));
                 const uint32_t kc = (cw == ctx ? cntc : c.cnt[cw]) - snap_b[cw];
-                if ((t.hdr[rel + w] >> 5) + 1u <= kc) general = true;
+                const uint32_t hw = t.hdr[rel + w];
+                if ((hw >> 5) + 1u <= kc && v3_valid_nodes(t, rel + w, c.dmax, (int) (hw & 31u), snap_b[cw] & (kRing - 1), kc) < (int) (hw & 31u)) general = true;
             }
         }
     }
@@ -560,9 +580,15 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
     c.suf[x & (kV3R - 1)] = (uint16_t) suffix;
     V3Live lv; lv.c = &c; lv.k = k; lv.upto = x;
     const uint32_t hdr = t.hdr[rel];
-    const int nvis = (int) (hdr & 31u);
-    if (!done && visited < D && nvis > 0) {
-        if (stale0) {                                                    // a slot the record read has been overwritten: replay literally
+    int nvis = (int) (hdr & 31u);
+    bool stale0 = false;
+    if (nvis > 0 && (hdr >> 5) + 1u <= kc0) {
+        const int nv = v3_valid_nodes(t, rel, c.dmax, nvis, snap_b[ctx] & (kRing - 1), kc0);
+        stale0 = nv == 0;
+        nvis = nv;
+    }
+    if (!done && visited < D && (nvis > 0 || stale0)) {
+        if (stale0) {                                                    // the record's first slot has been overwritten: replay literally
             r.n_slow++;
             uint32_t bn = 0;
             best = v3_main_live(lv, x, suffix, head, chk, ctx, D, &bn);
@@ -585,11 +611,15 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
             const int z = x + which, relz = rel + which;
             const uint32_t cz = v3_rb8(c.rbw, (uint32_t) z - 1);
             const uint32_t hz = t.hdr[relz];
-            const int nvz = (int) (hz & 31u);
-            if (nvz > 0 && (hz >> 5) + 1u <= c.cnt[cz] - snap_b[cz]) {   // stale lazy record
-                r.n_slow++;
-                if (v3_lazy_live(lv, z, best, depth)) return 0;
-                continue;
+            int nvz = (int) (hz & 31u);
+            const uint32_t kcz = c.cnt[cz] - snap_b[cz];
+            if (nvz > 0 && (hz >> 5) + 1u <= kcz) {                      // stale lazy record: cut it, or replay when its head is gone
+                nvz = v3_valid_nodes(t, relz, c.dmax, nvz, snap_b[cz] & (kRing - 1), kcz);
+                if (nvz == 0) {
+                    r.n_slow++;
+                    if (v3_lazy_live(lv, z, best, depth)) return 0;
+                    continue;
+                }
             }
             const uint32_t mine = v3_rb32(c.rbw, (uint32_t) z + at);
             int vis = 0;

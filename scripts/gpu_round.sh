@@ -1,0 +1,18 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, a bench line, the ncu launch list and one full ncu capture of the parse kernel.
+# usage: scripts/gpu_round.sh <tag> [quick]
+TAG=${1:-r1}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
+tail -2 gpurun_out/${TAG}_smoke.log
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
+tail -5 gpurun_out/${TAG}_pytest.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+if [ "$2" != "quick" ]; then
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_bench.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:zl_rolz_parse_v3 -c 1 -o gpurun_out/${TAG}_parse_v3 -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:zl_mtf_ctx -c 1 -o gpurun_out/${TAG}_mtf_ctx -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full2.log 2>&1
+  ls -la gpurun_out | tail -12
+fi
