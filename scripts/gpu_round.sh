@@ -4,8 +4,9 @@
 TAG=${1:-r1}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
-tail -2 gpurun_out/${TAG}_smoke.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; RC=$?; echo "smoke rc=$RC" >> gpurun_out/${TAG}_smoke.log
+tail -4 gpurun_out/${TAG}_smoke.log
+if [ $RC -ne 0 ]; then echo "smoke failed: trying the v2 parse / v1 mtf to localise"; ZLB_PARSE=2 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2; ZLB_MTF=1 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2; exit 1; fi
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
 tail -5 gpurun_out/${TAG}_pytest.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
