@@ -80,6 +80,15 @@ int zlb_encode_blocks(zlb_encoder* enc, const uint8_t* in, size_t n, uint8_t* ou
  * 16 bytes past n. */
 int zlb_encode_blocks_device(zlb_encoder* enc, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len);
 
+/* Split form for ONE stream sharded over several GPUs (contiguous block ranges per GPU).  The parse of a range does
+ * not depend on the MTF tables carried from the previous range, and on the carried level only for its first
+ * sub-block (src/libzling.cpp:185,261-266), so: submit = H2D + parse launch (returns at once, assumes the carried level
+ * is the requested one); then install the previous range's final state with zlb_encoder_set_state while the parse
+ * runs; complete = MTF ranks + Huffman + framing + D2H (re-parses the first block only if the carried level differs).
+ * zlb_encode_blocks(...) == submit + complete. */
+int zlb_encode_submit(zlb_encoder* enc, const uint8_t* in, size_t n);
+int zlb_encode_complete(zlb_encoder* enc, uint8_t* out, size_t out_cap, size_t* out_len);
+
 /* carried state: 65536 bytes of MTF tables (context-major, rank -> byte) followed by int32 LE current level */
 int zlb_encoder_get_state(zlb_encoder* enc, uint8_t* state /* ZLB_STATE_BYTES */);
 int zlb_encoder_set_state(zlb_encoder* enc, const uint8_t* state);

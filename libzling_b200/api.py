@@ -37,7 +37,7 @@ class SubBlock(C.Structure):
 
 EXPORTS = ["zlb_device_count", "zlb_create", "zlb_destroy", "zlb_max_blocks", "zlb_last_error", "zlb_version",
            "zlb_host_alloc", "zlb_host_free", "zlb_encode_bound", "zlb_encoder_begin", "zlb_encoder_end",
-           "zlb_encode_blocks", "zlb_encode_blocks_device", "zlb_encoder_get_state", "zlb_encoder_set_state",
+           "zlb_encode_blocks", "zlb_encode_blocks_device", "zlb_encode_submit", "zlb_encode_complete", "zlb_encoder_get_state", "zlb_encoder_set_state",
            "zlb_decoder_begin", "zlb_decoder_end", "zlb_decode_blocks", "zlb_get_stats", "zlb_debug_tokens",
            "zlb_debug_subblocks", "zlb_debug_huff_tables"]
 
@@ -73,6 +73,8 @@ def load():
     L.zlb_encoder_end.argtypes = [C.c_void_p]
     for f in (L.zlb_encode_blocks, L.zlb_encode_blocks_device):
         f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_encode_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.zlb_encode_complete.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.zlb_encoder_get_state.argtypes = [C.c_void_p, _u8p]
     L.zlb_encoder_set_state.argtypes = [C.c_void_p, _u8p]
     L.zlb_decoder_begin.restype = C.c_void_p
@@ -254,6 +256,21 @@ class Encoder:
         n = C.c_size_t(0)
         _check(load().zlb_encode_blocks_device(self._h, d_in_ptr, nbytes, d_out_ptr, out_cap, C.byref(n)))
         return n.value
+
+    def submit(self, data):
+        """split form, step 1: H2D + parse launch of a block range; returns immediately (see include/zlb.h)"""
+        a = _as_u8(data)
+        self._pending = a                     # keep the host buffer alive until complete()
+        _check(load().zlb_encode_submit(self._h, a.ctypes.data, a.size))
+
+    def complete(self):
+        """split form, step 2: MTF + Huffman + framing of the submitted range with the state installed by now"""
+        L = load()
+        out = np.empty(L.zlb_encode_bound(self._pending.size), dtype=np.uint8)
+        n = C.c_size_t(0)
+        _check(L.zlb_encode_complete(self._h, out.ctypes.data, out.size, C.byref(n)))
+        self._pending = None
+        return out[:n.value].tobytes()
 
     def get_state(self):
         s = np.zeros(65540, dtype=np.uint8)

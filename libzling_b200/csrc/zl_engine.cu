@@ -76,7 +76,9 @@ struct zlb_encoder {
     int level, cur_level;
     uint8_t* d_state[2];     // MTF rank->byte tables, ping-pong (input of a call stays intact until it succeeds)
     int cur;
+    size_t submitted_n;      // bytes handed to zlb_encode_submit and not yet completed (0 = nothing pending)
 };
+enum { MODE_ALL = 0, MODE_SUBMIT = 1, MODE_COMPLETE = 2 };
 struct zlb_decoder {
     zlb_ctx* ctx;
     uint8_t* d_state;
@@ -200,7 +202,7 @@ zlb_encoder* zlb_encoder_begin(zlb_ctx* c, int level) {
     cudaSetDevice(c->device);
     zlb_encoder* e = new (std::nothrow) zlb_encoder();
     if (!e) { fail(ZLB_E_NOMEM, "zlb_encoder_begin: out of host memory"); return nullptr; }
-    e->ctx = c; e->level = level; e->cur_level = level; e->cur = 0; e->d_state[0] = e->d_state[1] = nullptr;
+    e->ctx = c; e->level = level; e->cur_level = level; e->cur = 0; e->d_state[0] = e->d_state[1] = nullptr; e->submitted_n = 0;
     uint8_t init[65536];
     for (int ctx = 0; ctx < 256; ctx++) memcpy(init + ctx * 256, kMtfInit, 256);          // lz.cpp:106-111
     if (cudaMalloc(&e->d_state[0], 65536) != cudaSuccess || cudaMalloc(&e->d_state[1], 65536) != cudaSuccess ||
@@ -240,19 +242,32 @@ static inline bool incompressible(const SubBlock& s) {
     return (unsigned long long) s.olen * 20ull > (unsigned long long) (s.enc_end - s.enc_begin + 1) * 19ull;
 }
 
-static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after) {
+// mode MODE_ALL: the whole pipeline.  MODE_SUBMIT: plan + parse launch only, returns without synchronising (the
+// parse does not need the carried MTF state, and needs the carried level only for the first sub-block).
+// MODE_COMPLETE: the rest, after the carried state may have been replaced (zlb_encoder_set_state); block 0 is
+// parsed again only if the carried level turned out different from the one the submit assumed.
+static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after, int mode = MODE_ALL) {
     zlb_ctx* c = e->ctx;
     cudaStream_t st = c->stream;
     const int nb = (int) ((n + kBlockBytes - 1) / kBlockBytes);
     c->last_nblocks = nb;
     uint32_t launches = 0, parse_launches = 0, reparsed = 0;
-    for (int b = 0; b < nb; b++) {
-        c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
-        c->h_active[b] = 1;
-        memset(c->h_plan + (size_t) b * kMaxSubPerBlock, e->level, kMaxSubPerBlock);
+    bool skip_first_parse = false;
+    if (mode != MODE_COMPLETE) {
+        for (int b = 0; b < nb; b++) {
+            c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
+            c->h_active[b] = 1;
+            memset(c->h_plan + (size_t) b * kMaxSubPerBlock, e->level, kMaxSubPerBlock);
+        }
+        c->h_plan[0] = (uint8_t) e->cur_level;                    // current_level outlives blocks, libzling.cpp:185
+        CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
+    } else if (c->h_plan[0] == (uint8_t) e->cur_level) {
+        skip_first_parse = true;                                  // the submit's guess of the carried level was right
+    } else {
+        c->h_plan[0] = (uint8_t) e->cur_level;
+        for (int b = 0; b < nb; b++) c->h_active[b] = b == 0;
+        reparsed++;
     }
-    c->h_plan[0] = (uint8_t) e->cur_level;                        // current_level outlives blocks, libzling.cpp:185
-    CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
 
     uint8_t* state_in = e->d_state[e->cur];
     uint8_t* state_out = e->d_state[e->cur ^ 1];
@@ -263,6 +278,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
     int first_dirty = 0, final_level = e->cur_level;
     float ms_parse = 0, ms_mtf = 0, ms_build = 0;
     for (int pass = 0;; pass++) {
+        if (!(skip_first_parse && pass == 0)) {
         CU(cudaMemcpyAsync(c->d_plan, c->h_plan, (size_t) nb * kMaxSubPerBlock, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(c->ev[EV_PARSE0], st));
@@ -282,6 +298,9 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             zl_rolz_parse_v2_kernel<<<nb, kV2Threads, lay.total, st>>>(pa, W, dmax, lmax, e->level, c->d_v2c);
         }
         CU(cudaEventRecord(c->ev[EV_PARSE1], st));
+        launches += 2; parse_launches += 1;
+        }
+        if (mode == MODE_SUBMIT) { CU(cudaGetLastError()); return ZLB_OK; }
         if (c->mtf_version == 1) {
             zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
         } else {
@@ -303,7 +322,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         CU(cudaMemcpyAsync(c->h_ntok, c->d_ntok, nb * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        launches += 4; parse_launches += 1;
+        launches += 2;
         { float t; cudaEventElapsedTime(&t, c->ev[EV_PARSE0], c->ev[EV_PARSE1]); ms_parse += t;
           cudaEventElapsedTime(&t, c->ev[EV_PARSE1], c->ev[EV_MTF1]); ms_mtf += t;
           cudaEventElapsedTime(&t, c->ev[EV_MTF1], c->ev[EV_BUILD1]); ms_build += t; }
@@ -446,6 +465,49 @@ int zlb_encode_blocks(zlb_encoder* e, const uint8_t* in, size_t n, uint8_t* out,
     CU(cudaGetLastError());
     finish_stats(c, true);
     { float t = 0; if (cudaEventElapsedTime(&t, c->ev[EV_PACK1], c->ev[EV_END]) == cudaSuccess) c->stats.ms_d2h = t; cudaGetLastError(); }
+    *out_len = produced;
+    e->cur ^= 1; e->cur_level = level_after;
+    return ZLB_OK;
+}
+
+// split form of zlb_encode_blocks for one stream sharded over several GPUs: the parse of a block range does not
+// depend on the MTF state carried from the previous range, so it is launched first and the carried state is
+// installed (zlb_encoder_set_state) while it runs
+int zlb_encode_submit(zlb_encoder* e, const uint8_t* in, size_t n) {
+    if (!e || (n && !in)) return fail(ZLB_E_ARG, "zlb_encode_submit: null argument");
+    if (n == 0 || n > (size_t) e->ctx->max_blocks * kBlockBytes) return fail(ZLB_E_ARG, "zlb_encode_submit: size must be 1..max_blocks blocks");
+    if (e->submitted_n) return fail(ZLB_E_ARG, "zlb_encode_submit: a submit is already pending");
+    zlb_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    CU(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_in + n, 0, 64, c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+    size_t produced = 0;
+    int level_after = e->cur_level;
+    const int rc = encode_device(e, c->d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SUBMIT);
+    if (rc) return rc;
+    e->submitted_n = n;
+    return ZLB_OK;
+}
+int zlb_encode_complete(zlb_encoder* e, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!e || !out || !out_len) return fail(ZLB_E_ARG, "zlb_encode_complete: null argument");
+    if (!e->submitted_n) return fail(ZLB_E_ARG, "zlb_encode_complete: nothing was submitted");
+    zlb_ctx* c = e->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t n = e->submitted_n;
+    e->submitted_n = 0;
+    *out_len = 0;
+    size_t produced = 0;
+    int level_after = e->cur_level;
+    const int rc = encode_device(e, c->d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_COMPLETE);
+    if (rc) return rc;
+    if (produced > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_complete: output buffer too small");
+    CU(cudaMemcpyAsync(out, c->d_out, produced, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(c->ev[EV_END], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    finish_stats(c, true);
     *out_len = produced;
     e->cur ^= 1; e->cur_level = level_after;
     return ZLB_OK;

@@ -428,7 +428,28 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
             __syncwarp();
             if (lane == 0) {
                 const int cnt = min(kMtfChunk, n - base);
-                for (int q = 0; q < cnt; q++) {
+                int q = 0;
+                // two literals per step: the second one's table reads are issued together with the first one's and
+                // patched from registers where the first literal's swap touches them (the swap moves two entries)
+                for (; q + 1 < cnt; q += 2) {
+                    const uint32_t recA = s_rec[buf][q], recB = s_rec[buf][q + 1];
+                    const uint32_t bA = recA & 0xffu, bB = recB & 0xffu;
+                    const int iA = s_rank[bA], iBr = s_rank[bB];
+                    const int jA = mtf_next(iA);
+                    int iB = bB == bA ? jA : iBr;                       // assumes bB is not the byte A swaps with
+                    int jB = mtf_next(iB);
+                    const uint32_t oA = s_sym[jA];
+                    uint32_t oBr = s_sym[jB];
+                    if (bB == oA && bB != bA) { iB = iA; jB = mtf_next(iB); oBr = s_sym[jB]; }
+                    const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);
+                    s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;
+                    s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;
+                    s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;
+                    s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;
+                    tok[recA >> 8] = (uint32_t) iA | ((uint32_t) ctx << 10) | (bA << 22);
+                    tok[recB >> 8] = (uint32_t) iB | ((uint32_t) ctx << 10) | (bB << 22);
+                }
+                for (; q < cnt; q++) {
                     const uint32_t rec = s_rec[buf][q];
                     const uint32_t byte = rec & 0xffu;
                     const int i = s_rank[byte], jn = mtf_next(i);

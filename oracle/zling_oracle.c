@@ -429,13 +429,27 @@ int zo_huff_encode_subblock(const uint16_t* sym, int rlen, uint8_t* payload) {
 
 /* Whole stream.  Restates baidu::zling::Encode, src/libzling.cpp:174-291 (in-memory source/sink).
  * Returns compressed size (also when > cap: nothing is written past cap), -1 on bad level. */
+/* `state` (optional, 65540 bytes: 256x256 rank->byte MTF tables + int32 LE current level) is what the reference
+ * carries from block to block inside one Encode() call (m_mtf, src/libzling_lz.h:105; current_level,
+ * src/libzling.cpp:185): loaded before the first block and stored back after the last, so that a stream can be
+ * encoded range by range (tests of the multi-GPU carry hand-off). */
+long long zo_encode_range(const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap, uint8_t* state);
 long long zo_encode(const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap) {
+    return zo_encode_range(in, n, level, out, cap, NULL);
+}
+long long zo_encode_range(const uint8_t* in, size_t n, int level, uint8_t* out, size_t cap, uint8_t* state) {
     if (level < 0 || level > 4) return -1;
     zo_rolz* z = zo_rolz_new();
     uint16_t* sym = (uint16_t*) malloc(sizeof(uint16_t) * (ZO_SUB_SYMS + ZO_GUARD));
     uint8_t* payload = (uint8_t*) malloc(ZO_SUB_BYTES_MAX + ZO_GUARD + 8);
     zo_sink sink = { out, cap, 0 };
     int cur_level = level;                                               /* libzling.cpp:185 — outlives blocks */
+    if (state) {
+        memcpy(z->mtf_sym, state, 65536);
+        for (int c = 0; c < 256; c++) for (int r = 0; r < 256; r++) z->mtf_rank[c][z->mtf_sym[c][r]] = (uint8_t) r;
+        int32_t lv; memcpy(&lv, state + 65536, 4);
+        cur_level = lv;
+    }
 
     for (size_t off = 0; off < n; off += ZO_BLOCK_IN) {
         int ilen = (int) (n - off < ZO_BLOCK_IN ? n - off : ZO_BLOCK_IN);
@@ -455,6 +469,10 @@ long long zo_encode(const uint8_t* in, size_t n, int level, uint8_t* out, size_t
             for (int i = 0; i < olen; i++) sink_byte(&sink, payload[i]);
         }
         sink_byte(&sink, 0);
+    }
+    if (state) {
+        memcpy(state, z->mtf_sym, 65536);
+        int32_t lv = cur_level; memcpy(state + 65536, &lv, 4);
     }
     free(payload); free(sym); zo_rolz_free(z);
     return (long long) sink.n;
