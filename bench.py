@@ -267,7 +267,7 @@ def main():
             "kernel_ms": {"parse": round(pms, 3), "mtf": round(float(np.mean(mtf_ms)), 3), "huff_build": round(float(np.mean(build_ms)), 3),
                           "pack": round(float(np.mean(pack_ms)), 3), "wall_ms_per_step_incl_flush": round(wall_dev / args.steps * 1e3, 3)},
             "parse_counters": {k: int(last[k]) for k in ("tokens", "subblocks", "slow_main", "slow_lazy", "general_path", "window_hits", "windows", "reparsed_blocks",
-                                                          "cyc_spec", "cyc_resolve", "cyc_total")},
+                                                          "cyc_spec", "cyc_resolve", "cyc_total", "flagged")},
             "cpu_baseline": {"value": round(nbytes / 1e6 / cpu_dt, 3), "unit": "MB/s", "cores": 1, "kind": cpu_kind,
                              "sample": "the whole %d-byte workload once, single thread (the reference codec has no threading); %d host cores present" % (nbytes, os.cpu_count())},
         }

@@ -123,6 +123,7 @@ typedef struct {
     uint64_t cyc_resolve;     /* parse: SM cycles spent in the resolve phase, summed over blocks */
     uint64_t general_path;    /* parse: tokens resolved through the in-window candidate path instead of the frozen decision */
     uint64_t cyc_total;       /* parse v3: SM cycles from kernel start to end, summed over blocks */
+    uint64_t flagged;         /* parse v3: tokens whose decision carried a hazard flag (checked; most stay frozen) */
 } zlb_stats;
 int zlb_get_stats(const zlb_ctx* ctx, zlb_stats* out);
 

@@ -391,13 +391,13 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
     c->stats.tokens = ntok; c->stats.subblocks = nsub_total;
     c->stats.slow_main = c->stats.slow_lazy = c->stats.window_hits = c->stats.windows = 0;
     c->stats.cyc_spec = c->stats.cyc_resolve = c->stats.general_path = 0;
-    c->stats.cyc_total = 0;
+    c->stats.cyc_total = 0; c->stats.flagged = 0;
     if (c->parse_version == 3) {
         CU(cudaMemcpyAsync(&c->h_v3c, c->d_v3c, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->stats.slow_main = c->h_v3c.slow; c->stats.window_hits = c->h_v3c.linkwalk; c->stats.windows = c->h_v3c.windows;
         c->stats.cyc_spec = c->h_v3c.cyc_spec; c->stats.cyc_resolve = c->h_v3c.cyc_resolve; c->stats.general_path = c->h_v3c.general;
-        c->stats.cyc_total = c->h_v3c.cyc_total;
+        c->stats.cyc_total = c->h_v3c.cyc_total; c->stats.flagged = c->h_v3c.flagged;
     } else if (c->parse_version == 2) {
         CU(cudaMemcpyAsync(&c->h_v2c, c->d_v2c, sizeof(V2Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
     __shared__ __align__(16) uint8_t s_sym[256];          // rank -> byte
     __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
+    __shared__ __align__(16) uint8_t s_out[kMtfChunk];
     {
         const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
         for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
@@ -426,14 +427,15 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
             #pragma unroll
             for (int q = 0; q < kMtfChunk / 32; q++) { const int i = base + kMtfChunk + q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
             __syncwarp();
+            const int cnt = min(kMtfChunk, n - base);
             if (lane == 0) {
-                const int cnt = min(kMtfChunk, n - base);
                 int q = 0;
                 // two literals per step: the second one's table reads are issued together with the first one's and
-                // patched from registers where the first literal's swap touches them (the swap moves two entries)
+                // patched from registers where the first literal's swap touches them (the swap moves two entries).
+                // Ranks go to shared memory; the token words are written by all lanes after the chunk.
+                #pragma unroll 2
                 for (; q + 1 < cnt; q += 2) {
-                    const uint32_t recA = s_rec[buf][q], recB = s_rec[buf][q + 1];
-                    const uint32_t bA = recA & 0xffu, bB = recB & 0xffu;
+                    const uint32_t bA = s_rec[buf][q] & 0xffu, bB = s_rec[buf][q + 1] & 0xffu;
                     const int iA = s_rank[bA], iBr = s_rank[bB];
                     const int jA = mtf_next(iA);
                     int iB = bB == bA ? jA : iBr;                       // assumes bB is not the byte A swaps with
@@ -446,18 +448,21 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
                     s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;
                     s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;
                     s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;
-                    tok[recA >> 8] = (uint32_t) iA | ((uint32_t) ctx << 10) | (bA << 22);
-                    tok[recB >> 8] = (uint32_t) iB | ((uint32_t) ctx << 10) | (bB << 22);
+                    s_out[q] = (uint8_t) iA; s_out[q + 1] = (uint8_t) iB;
                 }
                 for (; q < cnt; q++) {
-                    const uint32_t rec = s_rec[buf][q];
-                    const uint32_t byte = rec & 0xffu;
+                    const uint32_t byte = s_rec[buf][q] & 0xffu;
                     const int i = s_rank[byte], jn = mtf_next(i);
                     const uint32_t other = s_sym[jn];
                     s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;
                     s_rank[other] = (uint8_t) i; s_rank[byte] = (uint8_t) jn;
-                    tok[rec >> 8] = (uint32_t) i | ((uint32_t) ctx << 10) | (byte << 22);
+                    s_out[q] = (uint8_t) i;
                 }
+            }
+            __syncwarp();
+            for (int q = lane; q < cnt; q += 32) {
+                const uint32_t rec = s_rec[buf][q];
+                tok[rec >> 8] = (uint32_t) s_out[q] | ((uint32_t) ctx << 10) | ((rec & 0xffu) << 22);
             }
             __syncwarp();
         }

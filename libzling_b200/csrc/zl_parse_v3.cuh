@@ -37,8 +37,11 @@ constexpr uint32_t kKeyInvalid = 0x80000000u;   // position cannot be probed (fi
 constexpr uint32_t kKeyMask    = 0x1fffffu;     // (context << 13) | hash slot
 
 // dec word 1 flag bits
-constexpr uint32_t kF_SELF = 1u << 16, kF_L1 = 1u << 17, kF_L2 = 1u << 18, kF_ST0 = 1u << 19, kF_ST1 = 1u << 20, kF_ST2 = 1u << 21;
-constexpr uint32_t kInsStart = 0x8000u, kInsSuperseded = 0x4000u;
+constexpr uint32_t kF_SELF = 1u << 16, kF_L1 = 1u << 17, kF_L2 = 1u << 18, kF_ST0 = 1u << 19, kF_ST1 = 1u << 20, kF_ST2 = 1u << 21, kF_NOPROBE = 1u << 22;
+constexpr uint32_t kF_ANY = 0x7fu << 16, kF_FORCE = 1u << 23;
+// per-position token mark (ins[]): ring head (12 bits) | kind << 12 | flags
+constexpr uint32_t kKindMatch = 1, kKindLit = 2, kKindWord0 = 3, kKindWord1 = 4;
+constexpr uint32_t kInsExplicit = 1u << 16, kInsSuperseded = 1u << 17;
 
 // ---- portable intrinsics -----------------------------------------------------------------------------------------
 ZL_HD uint32_t z3_funnel(uint32_t lo, uint32_t hi, uint32_t sh) {
@@ -104,7 +107,7 @@ ZL_HD uint32_t z3_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout -------------------------------------------------------------------------------------------
 struct V3Layout {
     int dmax, lmax;
-    int rb, key, link, blink, ins, suf, last, cnt, snap, mru, tab[2], total;
+    int rb, key, link, blink, ins, suf, tw, last, cnt, snap, mru, pcnt, tab[2], total;
     int t_hdr, t_node, t_eq, t_dec, t_size;          // offsets inside one table
 };
 __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
@@ -115,23 +118,25 @@ __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
     L.key   = take(4 * kV3R);
     L.link  = take(2 * kV3R);
     L.blink = take(2 * kV3R);
-    L.ins   = take(2 * kV3R);
+    L.ins   = take(4 * kV3R);
     L.suf   = take(2 * kV3R);
+    L.tw    = take(4 * kV3R);
     L.last  = take(4 * kV3Buckets);
     L.cnt   = take(4 * 256);
     L.snap  = take(4 * 256 * 3);
     L.mru   = take(4 * 256);
+    L.pcnt  = take(4 * 256 * 2);
     const int n = kV3W + 2;
     int t = 0;
     auto ttake = [&](int bytes) { int o = t; t += (bytes + 15) & ~15; return o; };
-    L.t_hdr = ttake(4 * n); L.t_node = ttake(4 * n * dmax); L.t_eq = ttake(20 * n * lmax); L.t_dec = ttake(8 * n);
+    L.t_hdr = ttake(4 * n); L.t_node = ttake(4 * n * dmax); L.t_eq = ttake(20 * n * lmax); L.t_dec = ttake(16 * n);
     L.t_size = t;
     L.tab[0] = take(t); L.tab[1] = take(t);
     L.total = at;
     return L;
 }
 
-struct V3Table { uint32_t* hdr; uint32_t* node; uint32_t* eq; uint2* dec; };
+struct V3Table { uint32_t* hdr; uint32_t* node; uint32_t* eq; uint4* dec; };
 
 struct V3Ctx {
     // block
@@ -140,23 +145,23 @@ struct V3Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan;
     // shared memory
     uint32_t* rbw;                              // input bytes, ring of kV3R bytes viewed as words
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* ins; uint16_t* suf;
-    uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* ins; uint16_t* suf; uint32_t* tw;
+    uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru; uint32_t* pcnt;
     uint8_t* tab0; int tab_stride, t_hdr, t_node, t_eq, t_dec;   // two tables, selected arithmetically (no dynamic struct indexing)
     int dmax, lmax;
 };
 ZL_HD V3Table v3_table(const V3Ctx& c, int j) {
     uint8_t* b = c.tab0 + (j & 1) * c.tab_stride;
     V3Table t;
-    t.hdr = (uint32_t*) (b + c.t_hdr); t.node = (uint32_t*) (b + c.t_node); t.eq = (uint32_t*) (b + c.t_eq); t.dec = (uint2*) (b + c.t_dec);
+    t.hdr = (uint32_t*) (b + c.t_hdr); t.node = (uint32_t*) (b + c.t_node); t.eq = (uint32_t*) (b + c.t_eq); t.dec = (uint4*) (b + c.t_dec);
     return t;
 }
 
 __host__ __device__ inline void v3_bind(V3Ctx& c, uint8_t* smem, const V3Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.ins = (uint16_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf);
+    c.blink = (uint16_t*) (smem + L.blink); c.ins = (uint32_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf); c.tw = (uint32_t*) (smem + L.tw);
     c.last = (uint32_t*) (smem + L.last); c.cnt = (uint32_t*) (smem + L.cnt); c.snap = (uint32_t*) (smem + L.snap);
-    c.mru = (uint32_t*) (smem + L.mru);
+    c.mru = (uint32_t*) (smem + L.mru); c.pcnt = (uint32_t*) (smem + L.pcnt);
     c.tab0 = smem + L.tab[0]; c.tab_stride = L.tab[1] - L.tab[0];
     c.t_hdr = L.t_hdr; c.t_node = L.t_node; c.t_eq = L.t_eq; c.t_dec = L.t_dec;
     c.dmax = L.dmax; c.lmax = L.lmax;
@@ -194,11 +199,19 @@ ZL_HD void v3_stage16(const V3Ctx& c, int src) {
 }
 
 // ---- SPEC phase A: key of a position -------------------------------------------------------------------------------
-ZL_HD void v3_key_position(const V3Ctx& c, int x) {
+// pcnt[j & 1][ctx] = positions first seen by SPEC(j) whose context byte is ctx: an upper bound of the inserts they can
+// make into that context (cleared by the caller before the pass)
+ZL_HD void v3_key_position(const V3Ctx& c, int x, int j) {
     uint32_t k = kKeyInvalid;
     if (x >= 2 && x + 273 < c.ilen) {
         const uint32_t h = z3_hash(v3_rb32(c.rbw, (uint32_t) x));
-        k = (v3_rb8(c.rbw, (uint32_t) x - 1) << 13) | (h & (kSlots - 1)) | (((h >> 13) & 0xffu) << 21);
+        const uint32_t ctx = v3_rb8(c.rbw, (uint32_t) x - 1);
+        k = (ctx << 13) | (h & (kSlots - 1)) | (((h >> 13) & 0xffu) << 21);
+#if defined(__CUDA_ARCH__)
+        atomicAdd(&c.pcnt[256 * (j & 1) + ctx], 1u);
+#else
+        c.pcnt[256 * (j & 1) + ctx]++;
+#endif
     }
     c.key[x & (kV3R - 1)] = k;
     c.ins[x & (kV3R - 1)] = 0;
@@ -334,6 +347,11 @@ ZL_HD void v3_spec_position(const V3Ctx& c, int j, int rel) {
 }
 
 // ---- SPEC phase E: the frozen decision of a main position -----------------------------------------------------------
+// dec[rel] (16 bytes, ONE shared-memory load per token for the resolver):
+//   .x  flen(9) | fbest(9) << 9 | fslot(12) << 18     frozen match length after the lazy veto / before it / ring slot of the best node
+//   .y  fhead(16) | flags << 16 | ctx << 24            frozen slot head (the insert's suffix), hazard flags, context byte in[x-1]
+//   .z  in[x-3] | (in[x-2] << 8 | in[x-1]) << 8        the word-MRU push made when a token ENDS at x (lz.cpp:163-166,183-185,190-191)
+//   .w  in[x] << 8 | in[x+1]                           the word tested at x when no match is taken (lz.cpp:172-185)
 ZL_HD bool v3_eq_hit(const uint32_t* eqw, uint32_t at) {                 // bytes [at, at+4) agree
     return (z3_funnel(eqw[at >> 5], eqw[(at >> 5) + 1], at & 31u) & 0xfu) == 0xfu;
 }
@@ -364,32 +382,71 @@ ZL_HD void v3_decide_position(const V3Ctx& c, int j, int rel, int level) {
     }
     // static hazard flags: which of x, x+1, x+2 have an earlier same-key position inside the live windows, and which
     // records read a ring slot that could be overwritten by the inserts of two windows
-    const uint32_t pend_max = 2u * kV3W + 4u;
+    // inserts into a context since base(j) <= positions of the live windows with that context byte (+2: the two
+    // look-ahead positions of window j-2, which SPEC(j-2) counted)
+    const uint32_t b3 = v3_rb32(c.rbw, (uint32_t) (x - 3));              // bytes x-3, x-2, x-1, x (zeros before the block)
+    const uint32_t nxt = v3_rb8(c.rbw, (uint32_t) x + 1);
+    const uint32_t ctx = (b3 >> 16) & 0xffu, ctx1 = b3 >> 24, ctx2 = nxt;
     uint32_t fl = 0;
+    const bool lazy_matters = fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow;
     if (c.link[x & (kV3R - 1)]) fl |= kF_SELF;
-    if (c.link[(x + 1) & (kV3R - 1)]) fl |= kF_L1;
-    if (c.link[(x + 2) & (kV3R - 1)]) fl |= kF_L2;
-    if (nvis > 0 && (hdr >> 5) + 1u <= pend_max) fl |= kF_ST0;
-    { const uint32_t h1 = t.hdr[rel + 1]; if ((h1 & 31u) && (h1 >> 5) + 1u <= pend_max) fl |= kF_ST1; }
-    { const uint32_t h2 = t.hdr[rel + 2]; if ((h2 & 31u) && (h2 >> 5) + 1u <= pend_max) fl |= kF_ST2; }
-    const uint32_t ctx = (c.key[x & (kV3R - 1)] >> 13) & 0xffu;
-    t.dec[rel] = make_uint2(flen | (fbest << 9) | (fslot << 18), fhead | fl | (ctx << 24));
+    if (nvis > 0 && (hdr >> 5) + 1u <= c.pcnt[ctx] + c.pcnt[256 + ctx] + 2u) fl |= kF_ST0;
+    if (lazy_matters) {
+        if (c.link[(x + 1) & (kV3R - 1)]) fl |= kF_L1;
+        { const uint32_t h1 = t.hdr[rel + 1]; if ((h1 & 31u) && (h1 >> 5) + 1u <= c.pcnt[ctx1] + c.pcnt[256 + ctx1] + 2u) fl |= kF_ST1; }
+        if (L2 > 0) {
+            if (c.link[(x + 2) & (kV3R - 1)]) fl |= kF_L2;
+            { const uint32_t h2 = t.hdr[rel + 2]; if ((h2 & 31u) && (h2 >> 5) + 1u <= c.pcnt[ctx2] + c.pcnt[256 + ctx2] + 2u) fl |= kF_ST2; }
+        }
+    }
+    const uint32_t kx = c.key[x & (kV3R - 1)];
+    if (kx & kKeyInvalid) fl |= kF_NOPROBE;                              // first two / last 273 bytes of the block: generic path
+    const uint32_t push = (b3 & 0xffu) | ((((b3 >> 8) & 0xffu) << 8 | ctx) << 8);
+    t.dec[rel] = make_uint4(flen | (fbest << 9) | (fslot << 18), fhead | fl | (ctx << 24), push, ((b3 >> 24) << 8) | nxt);
+}
+
+// ---- per-position token marks ------------------------------------------------------------------------------------------
+// ins[x] (u32): head(12) | kind << 12 | kInsExplicit | kInsSuperseded.  Every token that starts in the probe region
+// inserts (lz.cpp:227-230), so "kind != 0" is also the "x was inserted" mark the hazard checks and APPLY look at.
+ZL_HD uint32_t v3_kind(uint32_t m) { return (m >> 12) & 7u; }
+ZL_HD uint32_t v3_suffix_of(const V3Ctx& c, int y, uint32_t m) {         // suffix of the pending insert at y
+    if (m & kInsExplicit) return c.suf[y & (kV3R - 1)];
+    const V3Table t = v3_table(c, y / kV3W);
+    return t.dec[y - (y / kV3W) * kV3W].y & 0xffffu;                     // clean token: the frozen slot head
 }
 
 // ---- APPLY: scatter one position's insert into G --------------------------------------------------------------------
 ZL_HD void v3_apply_position(const V3Ctx& c, int y) {
     const uint32_t m = c.ins[y & (kV3R - 1)];
-    if (!(m & kInsStart)) return;
+    if (!v3_kind(m)) return;
     const uint32_t k = c.key[y & (kV3R - 1)];
     const uint32_t ctx = (k >> 13) & 0xffu, slot = k & (kSlots - 1), chk = k >> 21, head = m & (kRing - 1);
-    c.ring[(size_t) ctx * kRing + head] = ring_make((uint32_t) y, chk, c.suf[y & (kV3R - 1)]);
+    c.ring[(size_t) ctx * kRing + head] = ring_make((uint32_t) y, chk, v3_suffix_of(c, y, m));
     if (!(m & kInsSuperseded)) c.hash[(size_t) ctx * kSlots + slot] = (uint16_t) head;
 }
 
+// ---- EMIT: the token word of a marked position (all threads, after the window is resolved) ----------------------------
+ZL_HD uint32_t v3_token_of(const V3Ctx& c, int y, uint32_t m) {
+    const uint32_t kind = v3_kind(m);
+    if (kind == kKindLit) return tok_literal(v3_rb8(c.rbw, (uint32_t) y), v3_rb8(c.rbw, (uint32_t) y - 1), false);
+    if (kind == kKindWord0) return tok_word(0);
+    if (kind == kKindWord1) return tok_word(1);
+    if (m & kInsExplicit) return c.tw[y & (kV3R - 1)];
+    const V3Table t = v3_table(c, y / kV3W);
+    const uint32_t d0 = t.dec[y - (y / kV3W) * kV3W].x;
+    return tok_match(d0 & 511u, ((m & (kRing - 1)) - ((d0 >> 18) & (kRing - 1))) & (kRing - 1));
+}
+
+#if defined(ZL_V3_FLAG_HIST)
+static unsigned long long g_flag_hist[256];
+#endif
 // ---- RESOLVE --------------------------------------------------------------------------------------------------------
 struct V3Run {                       // resolver state carried across windows (one thread)
-    int ip, nt, nl, op, j, level, tok_begin, enc_begin;
-    unsigned long long n_general, n_slow, n_linkwalk;
+    int ip, op, j, level, tok_begin, enc_begin;
+    int prev_lit;                    // the previous token was a literal (its word-MRU push is unconditional)
+    int skip_push;                   // no push is pending on arrival (block start: the two raw bytes push nothing)
+    int tail;                        // ip reached the last 275 bytes: the rest is done by v3_resolve_tail
+    unsigned long long n_general, n_slow, n_linkwalk, n_flagged;
 };
 
 // GetCommonLength with both operands inside the byte ring
@@ -411,7 +468,7 @@ ZL_HD bool v3_link_hazard(const V3Ctx& c, int z, int base, int self) {
         if (!d) return false;
         y -= (int) d;
         if (y < base) return false;
-        if (y == self || (c.ins[y & (kV3R - 1)] & kInsStart)) return true;
+        if (y == self || v3_kind(c.ins[y & (kV3R - 1)])) return true;
     }
 }
 
@@ -425,8 +482,8 @@ ZL_HD uint64_t v3_live_entry(const V3Live& lv, uint32_t ctx, uint32_t n) {
     if (ord == 0 || ord > c.cnt[ctx] - done_k) return z3_ld_ring(c.ring + (size_t) ctx * kRing + n);
     for (int y = lv.upto; y >= lv.k * kV3W; y--) {          // newest first; a ring slot is written at most once per window
         const uint32_t m = c.ins[y & (kV3R - 1)];
-        if ((m & kInsStart) && (m & (kRing - 1)) == n && ((c.key[y & (kV3R - 1)] >> 13) & 0xffu) == ctx)
-            return ring_make((uint32_t) y, c.key[y & (kV3R - 1)] >> 21, c.suf[y & (kV3R - 1)]);
+        if (v3_kind(m) && (m & (kRing - 1)) == n && ((c.key[y & (kV3R - 1)] >> 13) & 0xffu) == ctx)
+            return ring_make((uint32_t) y, c.key[y & (kV3R - 1)] >> 21, v3_suffix_of(c, y, m));
     }
     return z3_ld_ring(c.ring + (size_t) ctx * kRing + n);
 }
@@ -434,7 +491,7 @@ ZL_HD uint32_t v3_live_head(const V3Live& lv, uint32_t key21, int before) {     
     const V3Ctx& c = *lv.c;
     for (int y = before - 1; y >= lv.k * kV3W; y--) {
         const uint32_t m = c.ins[y & (kV3R - 1)];
-        if ((m & kInsStart) && ((c.key[y & (kV3R - 1)] ^ key21) & kKeyMask) == 0) return m & (kRing - 1);
+        if (v3_kind(m) && ((c.key[y & (kV3R - 1)] ^ key21) & kKeyMask) == 0) return m & (kRing - 1);
     }
     return z3_ld_hash(c.hash + (size_t) (key21 >> 13) * kSlots + (key21 & (kSlots - 1)));
 }
@@ -484,14 +541,6 @@ ZL_HD int v3_main_live(const V3Live& lv, int x, uint32_t node, uint32_t head, ui
     return best;
 }
 
-ZL_HD void v3_close_subblock(const V3Ctx& c, V3Run& r) {
-    if (r.j < kMaxSubPerBlock) {
-        SubBlock sb; sb.tok_begin = (uint32_t) r.tok_begin; sb.tok_end = (uint32_t) r.nt; sb.enc_begin = (uint32_t) r.enc_begin;
-        sb.enc_end = (uint32_t) r.ip; sb.rlen = (uint32_t) r.op; sb.level = (uint32_t) r.level; sb.olen = 0; sb.bits_lo = 0;
-        c.sub[r.j] = sb;
-    }
-}
-
 // Leading nodes of a record whose ring slots have not been overwritten after `kc` further inserts into the context.
 // A record node that HAS been overwritten ends the reference's walk right there when it is not the first one (the
 // slot now holds a newer, i.e. larger, position: the "offset <= next offset" test of lz.cpp:264 fires), so a record
@@ -502,13 +551,14 @@ ZL_HD int v3_valid_nodes(const V3Table& t, int rel, int dmax, int nvis, uint32_t
     return i;
 }
 
-// probe + insert at token start x of window k (MatchAndUpdate); returns the match length (0 = none) and *midx
-ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t* midx) {
+// Flagged token start x of window k (some hazard flag set, or the level differs from the decision's): the full
+// MatchAndUpdate (lz.cpp:211-289) with the in-window candidates.  Books the insert (cnt / ins / suf, kInsExplicit)
+// and returns the match length (0 = none) and *midx.
+ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, const uint4& d, uint32_t* midx) {
     const V3Table t = v3_table(c, k);
     const int rel = x - k * kV3W;
     const int base = v3_base(k);
     const uint32_t* snap_b = c.snap + 256 * ((k + 2) % 3);               // counters at base(k)
-    const uint2 d = t.dec[rel];
     const uint32_t flen = d.x & 511u, fbest = (d.x >> 9) & 511u, fslot = (d.x >> 18) & (kRing - 1);
     const uint32_t fhead = d.y & 0xffffu, ctx = d.y >> 24;
     const int level = r.level;
@@ -517,7 +567,7 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
     const uint32_t cntc = c.cnt[ctx] + 1u, head = cntc & (kRing - 1);
     bool general = level != tlevel;
     const uint32_t kc0 = cntc - snap_b[ctx];
-    if (d.y & (kF_SELF | kF_L1 | kF_L2 | kF_ST0 | kF_ST1 | kF_ST2)) {
+    {
         const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (L2 > 0 ? 2 : 1) : 0;
         if (d.y & (kF_SELF | kF_L1 | kF_L2)) r.n_linkwalk++;
         if ((d.y & kF_SELF) && v3_link_hazard(c, x, base, -1)) general = true;
@@ -538,7 +588,7 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
     }
     if (!general) {                                                      // frozen decision stands
         c.cnt[ctx] = cntc;
-        c.ins[x & (kV3R - 1)] = (uint16_t) (head | kInsStart);
+        c.ins[x & (kV3R - 1)] = head | kInsExplicit;                     // kind is filled in by the caller
         c.suf[x & (kV3R - 1)] = (uint16_t) fhead;
         if (flen == 0) return 0;
         *midx = (head - fslot) & (kRing - 1);
@@ -560,10 +610,10 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
             y -= (int) dl;
             if (y < base) break;
             const uint32_t m = c.ins[y & (kV3R - 1)];
-            if (!(m & kInsStart)) continue;
+            if (!v3_kind(m)) continue;
             if (!have_suffix) {
                 suffix = m & (kRing - 1); have_suffix = true;
-                if (y >= k * kV3W) c.ins[y & (kV3R - 1)] = (uint16_t) (m | kInsSuperseded);   // same APPLY pass: x owns the slot head
+                if (y >= k * kV3W) c.ins[y & (kV3R - 1)] = m | kInsSuperseded;   // same APPLY pass: x owns the slot head
             }
             if (visited < D && !done) {
                 visited++;
@@ -571,12 +621,12 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
                     const int l = v3_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) y);
                     if (l > best) { best = l; bestslot = m & (kRing - 1); if (best == kMaxLen) done = true; }
                 }
-            } else if (have_suffix) break;
+            } else break;
         }
     }
     // insert (lz.cpp:227-230): pending until APPLY
     c.cnt[ctx] = cntc;
-    c.ins[x & (kV3R - 1)] = (uint16_t) (head | kInsStart);
+    c.ins[x & (kV3R - 1)] = head | kInsExplicit | (kKindLit << 12);      // provisional kind: the live replay must see x as inserted
     c.suf[x & (kV3R - 1)] = (uint16_t) suffix;
     V3Live lv; lv.c = &c; lv.k = k; lv.upto = x;
     const uint32_t hdr = t.hdr[rel];
@@ -629,7 +679,7 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
                 if (!dl) break;
                 y -= (int) dl;
                 if (y < base) break;
-                if (!(c.ins[y & (kV3R - 1)] & kInsStart)) continue;
+                if (!v3_kind(c.ins[y & (kV3R - 1)])) continue;
                 vis++;
                 if (v3_rb32(c.rbw, (uint32_t) y + at) == mine) return 0;
             }
@@ -643,63 +693,125 @@ ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, uint32_t*
     return best;
 }
 
-// tokens starting in window k (EncodeImpl, lz.cpp:139-195)
-ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel) {
-    const int wend = (k + 1) * kV3W < c.ilen ? (k + 1) * kV3W : c.ilen;
-    int ip = r.ip, nt = r.nt, nl = r.nl, op = r.op;
-    while (ip < wend) {
-        if (op + 1 >= kSubSymbols) {                                     // sub-block full (lz.cpp:153): close it, open the next
-            r.ip = ip; r.nt = nt; r.op = op;
-            v3_close_subblock(c, r);
-            r.j++;
-            r.level = c.plan[r.j < kMaxSubPerBlock ? r.j : kMaxSubPerBlock - 1];
-            for (int i = 0; i < 256; i++) c.mru[i] = 0;                  // lz.cpp:147
-            op = 0; r.tok_begin = nt; r.enc_begin = ip;
-        }
-        if (ip + kGuard < c.ilen) {                                      // lz.cpp:158
-            uint32_t midx = 0;
-            const int mlen = v3_probe(c, r, k, ip, tlevel, &midx);
-            if (mlen) {
-                c.tok[nt++] = tok_match((uint32_t) mlen, midx);
-                op += 2; ip += mlen;
-                const uint32_t b3 = v3_rb32(c.rbw, (uint32_t) ip - 3);
-                const uint32_t c3 = b3 & 0xffu, w = ((b3 >> 8) & 0xffu) << 8 | ((b3 >> 16) & 0xffu);
-                const uint32_t m = c.mru[c3];
-                if ((m & 0xffffu) != w) c.mru[c3] = w | (m << 16);       // lz.cpp:163-166
-                continue;
-            }
-        }
-        const uint32_t b = v3_rb32(c.rbw, (uint32_t) ip - 1);           // bytes ip-1, ip, ip+1 (ip >= 2 here)
-        const uint32_t c1 = b & 0xffu, cur = (b >> 8) & 0xffu;
-        if (ip + 1 < c.ilen) {                                           // lz.cpp:172-185
-            const uint32_t w = (cur << 8) | ((b >> 16) & 0xffu);
-            const uint32_t m = c.mru[c1];
-            if ((m & 0xffffu) == w) { c.tok[nt++] = tok_word(0); op++; ip += 2; continue; }
-            if ((m >> 16) == w) { c.tok[nt++] = tok_word(1); op++; ip += 2; c.mru[c1] = w | (m << 16); continue; }
-        }
-        c.tok[nt] = tok_literal(cur, c1, false);                         // lz.cpp:188-191
-        c.lit[nl++] = (uint32_t) nt;
-        nt++; op++; ip++;
-        {
-            const uint32_t c3 = v3_rb8(c.rbw, (uint32_t) ip - 3);
-            const uint32_t w = (c1 << 8) | cur;
-            c.mru[c3] = w | (c.mru[c3] << 16);
-        }
+// tokens of window k marked so far (the resolver needs a token index only when a sub-block closes)
+ZL_HD int v3_count_marks(const V3Ctx& c, int lo, int hi) {
+    int n = 0;
+    for (int y = lo; y < hi; y++) n += v3_kind(c.ins[y & (kV3R - 1)]) != 0;
+    return n;
+}
+ZL_HD void v3_close_subblock(const V3Ctx& c, V3Run& r, int nt) {
+    if (r.j < kMaxSubPerBlock) {
+        SubBlock sb; sb.tok_begin = (uint32_t) r.tok_begin; sb.tok_end = (uint32_t) nt; sb.enc_begin = (uint32_t) r.enc_begin;
+        sb.enc_end = (uint32_t) r.ip; sb.rlen = (uint32_t) r.op; sb.level = (uint32_t) r.level; sb.olen = 0; sb.bits_lo = 0;
+        c.sub[r.j] = sb;
     }
-    r.ip = ip; r.nt = nt; r.nl = nl; r.op = op;
+}
+ZL_HD void v3_rollover(const V3Ctx& c, V3Run& r, int nt) {                // sub-block full (lz.cpp:153): close it, open the next
+    v3_close_subblock(c, r, nt);
+    r.j++;
+    r.level = c.plan[r.j < kMaxSubPerBlock ? r.j : kMaxSubPerBlock - 1];
+    for (int i = 0; i < 256; i++) c.mru[i] = 0;                          // lz.cpp:147
+    r.op = 0; r.tok_begin = nt; r.enc_begin = r.ip;
+}
+
+// Tokens starting in window k (EncodeImpl, lz.cpp:139-195), probe region only (x + 275 < ilen).  The walker does
+// the minimum that is serial: one 16-byte decision load, the word-MRU push of the token that ended here, the
+// context's insert counter, and a per-position mark; token words, literal lists and bucket writes are produced
+// from the marks by all threads afterwards (v3_token_of / v3_apply_position).  nt0 = tokens emitted before window k.
+ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
+    if (r.tail) return;
+    const V3Table t = v3_table(c, k);
+    const int lim = c.ilen - kGuard;                                     // probes happen at x < lim (lz.cpp:158)
+    const int wend = (k + 1) * kV3W < lim ? (k + 1) * kV3W : lim;
+    int x = r.ip, op = r.op;
+    uint32_t prev_lit = (uint32_t) r.prev_lit, skip_push = (uint32_t) r.skip_push;
+    uint32_t force = r.level != tlevel ? kF_FORCE : 0u;
+    while (x < wend) {
+        const uint4 d = t.dec[x - k * kV3W];
+        {   // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
+            const uint32_t c3 = d.z & 0xffu, w = d.z >> 8;
+            const uint32_t m = c.mru[c3];
+            if (!skip_push && (prev_lit || (m & 0xffffu) != w)) c.mru[c3] = w | (m << 16);
+            skip_push = 0;
+        }
+        if (op + 1 >= kSubSymbols) {
+            r.ip = x; r.op = op;
+            v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));
+            op = 0;
+            force = r.level != tlevel ? kF_FORCE : 0u;
+        }
+        const uint32_t ctx = d.y >> 24;
+        uint32_t mark;
+        uint32_t flen = d.x & 511u;
+        if (((d.y & kF_ANY) | force) == 0) {                             // clean: the frozen decision stands
+            const uint32_t cn = c.cnt[ctx] + 1u;
+            c.cnt[ctx] = cn;
+            mark = cn & (kRing - 1);
+        } else {
+            r.n_flagged++;
+#if defined(ZL_V3_FLAG_HIST) && !defined(__CUDA_ARCH__)
+            g_flag_hist[((d.y >> 16) & 0x7fu) | (force ? 0x80u : 0u)]++;
+#endif
+            uint32_t midx = 0;
+            flen = (uint32_t) v3_probe(c, r, k, x, tlevel, d, &midx);
+            mark = c.ins[x & (kV3R - 1)] & (kRing - 1 | kInsExplicit);
+            if (flen) c.tw[x & (kV3R - 1)] = tok_match(flen, midx);
+        }
+        if (flen) {
+            c.ins[x & (kV3R - 1)] = mark | (kKindMatch << 12);
+            op += 2; x += (int) flen; prev_lit = 0;
+            continue;
+        }
+        const uint32_t w1 = d.w, m1 = c.mru[ctx];                        // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
+        if ((m1 & 0xffffu) == w1) { c.ins[x & (kV3R - 1)] = mark | (kKindWord0 << 12); op++; x += 2; prev_lit = 0; }
+        else if ((m1 >> 16) == w1) { c.ins[x & (kV3R - 1)] = mark | (kKindWord1 << 12); op++; x += 2; prev_lit = 0; }   // its MRU update = the push at x + 2
+        else { c.ins[x & (kV3R - 1)] = mark | (kKindLit << 12); op++; x += 1; prev_lit = 1; }
+    }
+    r.ip = x; r.op = op; r.prev_lit = (int) prev_lit; r.skip_push = (int) skip_push;
+    if (x >= lim) r.tail = 1;
+}
+
+// The last 275 bytes of the block (no probe, no insert: lz.cpp:158) and blocks shorter than that: plain serial
+// code, tokens written directly.  nt / nl = tokens / literals emitted so far.
+ZL_HD void v3_resolve_tail(const V3Ctx& c, V3Run& r, int* nt_io, int* nl_io) {
+    int nt = *nt_io, nl = *nl_io;
+    int ip = r.ip, op = r.op;
+    const uint8_t* in = c.in;
+    bool pending_push = !r.skip_push && ip >= 3;
+    while (ip < c.ilen) {
+        if (pending_push) {
+            const uint32_t c3 = in[ip - 3], w = ((uint32_t) in[ip - 2] << 8) | in[ip - 1];
+            const uint32_t m = c.mru[c3];
+            if (r.prev_lit || (m & 0xffffu) != w) c.mru[c3] = w | (m << 16);
+        }
+        pending_push = true;
+        if (op + 1 >= kSubSymbols) { r.ip = ip; r.op = op; v3_rollover(c, r, nt); op = 0; }
+        const uint32_t c1 = in[ip - 1], cur = in[ip];
+        if (ip + 1 < c.ilen) {
+            const uint32_t w = (cur << 8) | in[ip + 1];
+            const uint32_t m = c.mru[c1];
+            if ((m & 0xffffu) == w) { c.tok[nt++] = tok_word(0); op++; ip += 2; r.prev_lit = 0; continue; }
+            if ((m >> 16) == w) { c.tok[nt++] = tok_word(1); op++; ip += 2; r.prev_lit = 0; continue; }
+        }
+        c.tok[nt] = tok_literal(cur, c1, false);
+        c.lit[nl++] = (uint32_t) nt;
+        nt++; op++; ip++; r.prev_lit = 1;
+    }
+    r.ip = ip; r.op = op;
+    *nt_io = nt; *nl_io = nl;
 }
 
 #if defined(__CUDACC__)
-struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows, cyc_resolve, cyc_spec, cyc_total; };
+struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows, cyc_resolve, cyc_spec, cyc_total, flagged; };
 
 __device__ __forceinline__ void v3_bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kV3Prod) : "memory"); }
 
-// ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps 1..16 = producers --------
+// ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps 1..15 = producers --------
 __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, V3Counters* counters) {
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ int s_level, s_tlevel[2];
+    __shared__ int s_level, s_tlevel[2], s_nt, s_nl, s_wtok[kV3Threads / 32], s_wlit[kV3Threads / 32];
     const V3Layout L = v3_layout(dmax, lmax);
     V3Ctx c;
     v3_bind(c, smem_raw, L);
@@ -711,23 +823,25 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     const bool producer = tid >= 32;
     const int ptid = tid - 32;
 
-    for (int i = tid; i < 256; i += kV3Threads) { c.cnt[i] = 0; c.mru[i] = 0; c.snap[i] = 0; c.snap[256 + i] = 0; c.snap[512 + i] = 0; }
+    for (int i = tid; i < 256; i += kV3Threads) { c.cnt[i] = 0; c.mru[i] = 0; c.snap[i] = 0; c.snap[256 + i] = 0; c.snap[512 + i] = 0; c.pcnt[i] = 0; c.pcnt[256 + i] = 0; }
     for (int i = tid; i < kV3Buckets; i += kV3Threads) c.last[i] = 0;
     for (int i = tid; i < kV3R; i += kV3Threads) { c.ins[i] = 0; c.link[i] = 0; c.blink[i] = 0; c.key[i] = kKeyInvalid; }
 
     V3Run r;
-    r.ip = 0; r.nt = 0; r.nl = 0; r.op = 0; r.j = 0; r.level = c.plan[0]; r.tok_begin = 0; r.enc_begin = 0;
-    r.n_general = 0; r.n_slow = 0; r.n_linkwalk = 0;
+    r.ip = 0; r.op = 0; r.j = 0; r.level = c.plan[0]; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
+    r.n_general = 0; r.n_slow = 0; r.n_linkwalk = 0; r.n_flagged = 0;
     long long cyc_res = 0, cyc_spec = 0;
     const long long t_begin = clock64();
     if (tid == 0) {
+        int nt = 0;
         for (int first = 0; first < 2; first++) {                        // first two bytes raw, lz.cpp:150-151
-            if (r.ip == first && r.ip < ilen) { c.tok[r.nt++] = tok_literal(c.in[r.ip], 0, true); r.op++; r.ip++; }
+            if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(c.in[r.ip], 0, true); r.op++; r.ip++; }
         }
-        s_level = r.level;
+        s_level = r.level; s_nt = nt; s_nl = 0;
     }
     __syncthreads();
-    const int nwin = (ilen + kV3W - 1) / kV3W;
+    const int lim = ilen - kGuard;
+    const int nwin = lim > 2 ? (lim + kV3W - 1) / kV3W : 0;              // windows that contain probe positions
     int staged_hi = -16;                                                 // bytes [.., staged_hi) are in the ring (first window also stages 16 lead bytes)
 
     for (int k = -1; k < nwin; k++) {
@@ -738,9 +852,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
                 const long long t0 = clock64();
                 const int hi = v3_stage_hi(j);
                 for (int src = staged_hi + ptid * 16; src < hi; src += kV3Prod * 16) v3_stage16(c, src);
+                if (ptid < 256) c.pcnt[256 * (j & 1) + ptid] = 0;
                 v3_bar_producers();
                 const int nlo = v3_new_lo(j), nhi = v3_new_hi(j);
-                for (int x = nlo + ptid; x < nhi; x += kV3Prod) v3_key_position(c, x);
+                for (int x = nlo + ptid; x < nhi; x += kV3Prod) v3_key_position(c, x, j);
                 v3_bar_producers();
                 if (ptid < 32) {                                         // bucket chains, 32 positions per round in increasing order
                     for (int x0 = nlo; x0 < nhi; x0 += 32) {
@@ -772,28 +887,49 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
             }
         } else if (tid == 0 && k >= 0) {
             const long long t0 = clock64();
-            v3_resolve_window(c, r, k, s_tlevel[k & 1]);
+            v3_resolve_window(c, r, k, s_tlevel[k & 1], s_nt);
             cyc_res += clock64() - t0;
         }
         __syncthreads();
-        if (k >= 0) {                                                    // APPLY(k) + counter snapshot k+1
-            const int lo = k * kV3W, hi = min((k + 1) * kV3W, ilen);
-            for (int y = lo + tid; y < hi; y += kV3Threads) v3_apply_position(c, y);
+        if (k >= 0) {                                                    // APPLY(k) + EMIT(k) + counter snapshot k+1
+            const int lo = k * kV3W;
+            const int y = lo + tid;                                      // kV3Threads >= kV3W: one position per thread
+            uint32_t m = 0;
+            if (tid < kV3W && y < ilen) { m = c.ins[y & (kV3R - 1)]; if (v3_kind(m)) v3_apply_position(c, y); }
+            const uint32_t kind = v3_kind(m);
+            const uint32_t bt = __ballot_sync(0xffffffffu, kind != 0), bl = __ballot_sync(0xffffffffu, kind == kKindLit);
+            if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); }
+            __syncthreads();
+            int tb = s_nt, lb = s_nl, ttot = 0, ltot = 0;
+            for (int w = 0; w < kV3Threads / 32; w++) {
+                const int tw = s_wtok[w], lw = s_wlit[w];
+                if (w < warp) { tb += tw; lb += lw; }
+                ttot += tw; ltot += lw;
+            }
+            if (kind) {
+                const int ti = tb + __popc(bt & ((1u << lane) - 1u));
+                c.tok[ti] = v3_token_of(c, y, m);
+                if (kind == kKindLit) c.lit[lb + __popc(bl & ((1u << lane) - 1u))] = (uint32_t) ti;
+            }
             uint32_t* snap = c.snap + 256 * ((k + 1) % 3);
             for (int i = tid; i < 256; i += kV3Threads) snap[i] = c.cnt[i];
-            if (tid == 0) s_level = r.level;
+            __syncthreads();
+            if (tid == 0) { s_level = r.level; s_nt += ttot; s_nl += ltot; }
         }
         staged_hi = v3_stage_hi(k + 1);
         __syncthreads();
     }
     if (tid == 0) {
-        if (ilen > 0) v3_close_subblock(c, r);
-        a.nsub[b] = ilen > 0 ? r.j + 1 : 0; a.ntok[b] = r.nt; a.nlit[b] = r.nl;
+        int nt = s_nt, nl = s_nl;
+        v3_resolve_tail(c, r, &nt, &nl);
+        if (ilen > 0) v3_close_subblock(c, r, nt);
+        a.nsub[b] = ilen > 0 ? r.j + 1 : 0; a.ntok[b] = nt; a.nlit[b] = nl;
         if (counters) {
-            atomicAdd(&counters->tokens, (unsigned long long) r.nt);
+            atomicAdd(&counters->tokens, (unsigned long long) nt);
             atomicAdd(&counters->general, r.n_general);
             atomicAdd(&counters->slow, r.n_slow);
             atomicAdd(&counters->linkwalk, r.n_linkwalk);
+            atomicAdd(&counters->flagged, r.n_flagged);
             atomicAdd(&counters->windows, (unsigned long long) nwin);
             atomicAdd(&counters->cyc_resolve, (unsigned long long) cyc_res);
             atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));

@@ -60,17 +60,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < kV3R; i++) c.key[i] = kKeyInvalid;
 
     V3Run r; memset(&r, 0, sizeof r);
-    r.level = plan[0];
+    r.level = plan[0]; r.skip_push = 1;
+    int nt = 0, nl = 0;
     for (int first = 0; first < 2; first++)
-        if (r.ip == first && r.ip < ilen) { c.tok[r.nt++] = tok_literal(in[r.ip], 0, true); r.op++; r.ip++; }
+        if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(in[r.ip], 0, true); r.op++; r.ip++; }
     int s_level = r.level, s_tlevel[2] = { 0, 0 };
-    const int nwin = (ilen + kV3W - 1) / kV3W;
+    const int lim = ilen - kGuard;
+    const int nwin = lim > 2 ? (lim + kV3W - 1) / kV3W : 0;
     int staged_hi = -16;
     auto spec = [&](int j, int tlevel) {
         const int hi = v3_stage_hi(j);
         for (int src = staged_hi; src < hi; src += 16) v3_stage16(c, src);
         const int nlo = v3_new_lo(j), nhi = v3_new_hi(j);
-        for (int x = nlo; x < nhi; x++) v3_key_position(c, x);
+        for (int i = 0; i < 256; i++) c.pcnt[256 * (j & 1) + i] = 0;
+        for (int x = nlo; x < nhi; x++) v3_key_position(c, x, j);
         v3_bucket_pass_serial(c, nlo, nhi);
         for (int rel = 0; rel < kV3W + 2; rel++) v3_spec_position(c, j, rel);
         for (int x = nlo; x < nhi; x++) v3_link_position(c, x, v3_base(j));
@@ -80,19 +83,28 @@ int main(int argc, char** argv) {
     for (int k = -1; k < nwin; k++) {
         const int tlevel_next = s_level;
         if (order == 0 && k + 1 < nwin) spec(k + 1, tlevel_next);
-        if (k >= 0) v3_resolve_window(c, r, k, s_tlevel[k & 1]);
+        if (k >= 0) v3_resolve_window(c, r, k, s_tlevel[k & 1], nt);
         if (order != 0 && k + 1 < nwin) spec(k + 1, tlevel_next);
-        if (k >= 0) {
-            const int lo = k * kV3W, hi = (k + 1) * kV3W < ilen ? (k + 1) * kV3W : ilen;
-            for (int y = lo; y < hi; y++) v3_apply_position(c, y);
+        if (k >= 0) {                                                    // APPLY + EMIT, position order = token order
+            const int lo = k * kV3W;
+            for (int y = lo; y < lo + kV3W && y < ilen; y++) {
+                const uint32_t m = c.ins[y & (kV3R - 1)];
+                if (!v3_kind(m)) continue;
+                v3_apply_position(c, y);
+                c.tok[nt] = v3_token_of(c, y, m);
+                if (v3_kind(m) == kKindLit) c.lit[nl++] = (uint32_t) nt;
+                nt++;
+            }
             uint32_t* snap = c.snap + 256 * ((k + 1) % 3);
             for (int i = 0; i < 256; i++) snap[i] = c.cnt[i];
             s_level = r.level;
         }
         staged_hi = v3_stage_hi(k + 1);
     }
-    if (ilen > 0) v3_close_subblock(c, r);
+    v3_resolve_tail(c, r, &nt, &nl);
+    if (ilen > 0) v3_close_subblock(c, r, nt);
     const int nsub = ilen > 0 ? r.j + 1 : 0;
+    const int sim_nt = nt;
 
     // ---------------- oracle
     zo_rolz* z = zo_rolz_new();
@@ -123,7 +135,7 @@ int main(int argc, char** argv) {
             const uint32_t g = tok[t];
             Tok got = { 0, tok_sym(g), tok_sym(g) >= 258 ? tok_aux(g) : 0, 0 };
             if (tok_sym(g) < 256) got.sym = tok_byte(g);
-            if ((long long) t >= r.nt || got.sym != want.sym || got.aux != want.aux || (s < 256) != (tok_sym(g) < 256)) {
+            if ((long long) t >= sim_nt || got.sym != want.sym || got.aux != want.aux || (s < 256) != (tok_sym(g) < 256)) {
                 fprintf(stderr, "token %zu (sub-block %d, pos %u) differs: sim sym %u aux %u | oracle sym %u aux %u\n", t, j, want.pos, got.sym, got.aux, want.sym, want.aux);
                 bad = (long long) t;
                 break;
@@ -131,9 +143,13 @@ int main(int argc, char** argv) {
         }
         j++;
     }
-    if (bad < 0 && ((long long) t != r.nt || j != nsub)) { fprintf(stderr, "count mismatch: sim %d tokens %d subs, oracle %zu tokens %d subs\n", r.nt, nsub, t, j); bad = 0; }
+    if (bad < 0 && ((long long) t != sim_nt || j != nsub)) { fprintf(stderr, "count mismatch: sim %d tokens %d subs, oracle %zu tokens %d subs\n", sim_nt, nsub, t, j); bad = 0; }
     zo_rolz_free(z);
-    printf("%s level %d order %d: %d bytes, %d tokens, %d sub-blocks, general %llu (%.2f%%), slow %llu, linkwalk %llu (%.2f%%) -> %s\n", argv[1], level, order, ilen, r.nt, nsub,
-           r.n_general, 100.0 * r.n_general / (r.nt ? r.nt : 1), r.n_slow, r.n_linkwalk, 100.0 * r.n_linkwalk / (r.nt ? r.nt : 1), bad < 0 ? "OK" : "MISMATCH");
+    printf("%s level %d order %d: %d bytes, %d tokens, %d sub-blocks, flagged %llu (%.2f%%), general %llu (%.2f%%), slow %llu, linkwalk %llu -> %s\n", argv[1], level, order, ilen,
+           sim_nt, nsub, r.n_flagged, 100.0 * r.n_flagged / (sim_nt ? sim_nt : 1), r.n_general, 100.0 * r.n_general / (sim_nt ? sim_nt : 1), r.n_slow, r.n_linkwalk,
+           bad < 0 ? "OK" : "MISMATCH");
+#if defined(ZL_V3_FLAG_HIST)
+    for (int i = 0; i < 256; i++) if (g_flag_hist[i]) printf("  flags %02x: %llu\n", i, g_flag_hist[i]);
+#endif
     return bad < 0 ? 0 : 1;
 }
