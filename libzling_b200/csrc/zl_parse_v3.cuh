@@ -21,7 +21,7 @@
 //
 // SPEC(k+1) and RESOLVE(k) touch disjoint state, so they run concurrently; every function of the algorithm is
 // plain scalar code marked ZL_HD, and tests/cxx/parse_v3_sim.cu replays the same phases on the host against the
-// oracle (the GPU box then only has to confirm the synchronisation).  Bit-exactness argument: DESIGN.md §4.
+// CPU checker (the GPU box then only has to confirm the synchronisation).  Bit-exactness argument: DESIGN.md §4.
 #pragma once
 #include "zl_kernels.cuh"
 

@@ -13,7 +13,7 @@ independent.  So every rank
   4. takes part in ONE gather of the framed outputs to rank 0, which concatenates them in block order.
 
 `enc` is anything with submit / set_state / complete / get_state (libzling_b200.Encoder on a GPU; the tests drive the
-same code with a CPU stand-in built on the oracle over gloo).
+same code with a CPU stand-in over gloo).
 """
 import numpy as np
 
