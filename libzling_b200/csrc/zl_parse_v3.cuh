@@ -325,6 +325,9 @@ ZL_HD void v3_spec_position(const V3Ctx& c, int j, int rel) {
         uint64_t e = z3_ld_ring(rc + node);
         for (int i = 0; i < c.dmax; i++) {
             const uint32_t q = ring_pos(e);
+            const uint32_t nxt = ring_suffix(e);
+            // the next chain node is fetched while this one's bytes are compared (independent loads overlap)
+            const uint64_t e2 = nxt != (uint32_t) kNil ? z3_ld_ring(rc + nxt) : 0ull;
             int len = 0;
             if (i < c.lmax) {
                 uint32_t* eq5 = t.eq + (size_t) (rel * c.lmax + i) * 5;
@@ -335,10 +338,8 @@ ZL_HD void v3_spec_position(const V3Ctx& c, int j, int rel) {
             }
             t.node[rel * c.dmax + i] = (uint32_t) len | (node << 9);
             nvis = i + 1;
-            const uint32_t nxt = ring_suffix(e);
             if (nxt == (uint32_t) kNil) break;
             dmin = min(dmin, v3_ring_dist(nxt, head_b));
-            const uint64_t e2 = z3_ld_ring(rc + nxt);
             if (q <= ring_pos(e2)) break;
             node = nxt; e = e2;
         }
