@@ -447,7 +447,7 @@ struct V3Run {                       // resolver state carried across windows (o
     int prev_lit;                    // the previous token was a literal (its word-MRU push is unconditional)
     int skip_push;                   // no push is pending on arrival (block start: the two raw bytes push nothing)
     int tail;                        // ip reached the last 275 bytes: the rest is done by v3_resolve_tail
-    unsigned long long n_general, n_slow, n_linkwalk, n_flagged;
+    uint32_t n_general, n_slow, n_linkwalk, n_flagged;
 };
 
 // GetCommonLength with both operands inside the byte ring
@@ -552,49 +552,54 @@ ZL_HD int v3_valid_nodes(const V3Table& t, int rel, int dmax, int nvis, uint32_t
     return i;
 }
 
-// Flagged token start x of window k (some hazard flag set, or the level differs from the decision's): the full
-// MatchAndUpdate (lz.cpp:211-289) with the in-window candidates.  Books the insert (cnt / ins / suf, kInsExplicit)
-// and returns the match length (0 = none) and *midx.
-ZL_HD int v3_probe(const V3Ctx& c, V3Run& r, int k, int x, int tlevel, const uint4& d, uint32_t* midx) {
-    const V3Table t = v3_table(c, k);
-    const int rel = x - k * kV3W;
-    const int base = v3_base(k);
-    const uint32_t* snap_b = c.snap + 256 * ((k + 2) % 3);               // counters at base(k)
-    const uint32_t flen = d.x & 511u, fbest = (d.x >> 9) & 511u, fslot = (d.x >> 18) & (kRing - 1);
-    const uint32_t fhead = d.y & 0xffffu, ctx = d.y >> 24;
-    const int level = r.level;
-    const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
+// per-window constants of the resolver (hoisted out of the token loop)
+struct V3Win {
+    V3Table t; int k, base, D, L1, L2, tlevel;
+    const uint32_t* snap_b;          // insert counters at base(k)
+};
+ZL_HD V3Win v3_window(const V3Ctx& c, int k, int level, int tlevel) {
+    V3Win w; w.t = v3_table(c, k); w.k = k; w.base = v3_base(k);
+    w.D = depth_main(level); w.L1 = depth_lazy1(level); w.L2 = depth_lazy2(level); w.tlevel = tlevel;
+    w.snap_b = c.snap + 256 * ((k + 2) % 3);
+    return w;
+}
 
-    const uint32_t cntc = c.cnt[ctx] + 1u, head = cntc & (kRing - 1);
-    bool general = level != tlevel;
-    const uint32_t kc0 = cntc - snap_b[ctx];
-    {
-        const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (L2 > 0 ? 2 : 1) : 0;
-        if (d.y & (kF_SELF | kF_L1 | kF_L2)) r.n_linkwalk++;
-        if ((d.y & kF_SELF) && v3_link_hazard(c, x, base, -1)) general = true;
-        if (nlazy >= 1 && (d.y & kF_L1) && v3_link_hazard(c, x + 1, base, x)) general = true;
-        if (nlazy >= 2 && (d.y & kF_L2) && v3_link_hazard(c, x + 2, base, x)) general = true;
-        if (d.y & kF_ST0) {
-            const uint32_t h0 = t.hdr[rel];
-            if ((h0 >> 5) + 1u <= kc0 && v3_valid_nodes(t, rel, c.dmax, (int) (h0 & 31u), snap_b[ctx] & (kRing - 1), kc0) < (int) (h0 & 31u)) general = true;
-        }
-        for (int w = 1; w <= nlazy; w++) {
-            if (d.y & (w == 1 ? kF_ST1 : kF_ST2)) {
-                const uint32_t cw = v3_rb8(c.rbw, (uint32_t) (x + w - 1));
-                const uint32_t kc = (cw == ctx ? cntc : c.cnt[cw]) - snap_b[cw];
-                const uint32_t hw = t.hdr[rel + w];
-                if ((hw >> 5) + 1u <= kc && v3_valid_nodes(t, rel + w, c.dmax, (int) (hw & 31u), snap_b[cw] & (kRing - 1), kc) < (int) (hw & 31u)) general = true;
+// Does any hazard flag of the decision at x actually hold?  (cn = insert counter of x's context INCLUDING x's insert)
+ZL_HD bool v3_hazard(const V3Ctx& c, const V3Win& w, int x, const uint4& d, uint32_t cn) {
+    const int rel = x - w.k * kV3W;
+    const uint32_t fbest = (d.x >> 9) & 511u, ctx = d.y >> 24;
+    const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (w.L2 > 0 ? 2 : 1) : 0;
+    if ((d.y & kF_SELF) && v3_link_hazard(c, x, w.base, -1)) return true;
+    if (nlazy >= 1 && (d.y & kF_L1) && v3_link_hazard(c, x + 1, w.base, x)) return true;
+    if (nlazy >= 2 && (d.y & kF_L2) && v3_link_hazard(c, x + 2, w.base, x)) return true;
+    if (d.y & kF_ST0) {
+        const uint32_t h0 = w.t.hdr[rel], kc0 = cn - w.snap_b[ctx];
+        if ((h0 >> 5) + 1u <= kc0 && v3_valid_nodes(w.t, rel, c.dmax, (int) (h0 & 31u), w.snap_b[ctx] & (kRing - 1), kc0) < (int) (h0 & 31u)) return true;
+    }
+    if (d.y & (kF_ST1 | kF_ST2)) {
+        for (int q = 1; q <= nlazy; q++) {
+            if (d.y & (q == 1 ? kF_ST1 : kF_ST2)) {
+                const uint32_t cw = q == 1 ? (d.w >> 8) : (d.w & 0xffu);      // context of x+1 is in[x], of x+2 is in[x+1]
+                const uint32_t kc = (cw == ctx ? cn : c.cnt[cw]) - w.snap_b[cw];
+                const uint32_t hw = w.t.hdr[rel + q];
+                if ((hw >> 5) + 1u <= kc && v3_valid_nodes(w.t, rel + q, c.dmax, (int) (hw & 31u), w.snap_b[cw] & (kRing - 1), kc) < (int) (hw & 31u)) return true;
             }
         }
     }
-    if (!general) {                                                      // frozen decision stands
-        c.cnt[ctx] = cntc;
-        c.ins[x & (kV3R - 1)] = head | kInsExplicit;                     // kind is filled in by the caller
-        c.suf[x & (kV3R - 1)] = (uint16_t) fhead;
-        if (flen == 0) return 0;
-        *midx = (head - fslot) & (kRing - 1);
-        return (int) flen;
-    }
+    return false;
+}
+
+// Token start x of window k whose frozen decision does not stand (a hazard holds, or the level differs): the full
+// MatchAndUpdate (lz.cpp:211-289) with the in-window candidates.  Books the insert (cnt / ins / suf, kInsExplicit)
+// and returns the match length (0 = none) and *midx.
+ZL_HD int v3_probe_general(const V3Ctx& c, V3Run& r, const V3Win& w, int x, const uint4& d, uint32_t* midx) {
+    const V3Table& t = w.t;
+    const int k = w.k, rel = x - k * kV3W, base = w.base;
+    const uint32_t* snap_b = w.snap_b;
+    const uint32_t fhead = d.y & 0xffffu, ctx = d.y >> 24;
+    const int D = w.D, L1 = w.L1, L2 = w.L2;
+    const uint32_t cntc = c.cnt[ctx] + 1u, head = cntc & (kRing - 1);
+    const uint32_t kc0 = cntc - snap_b[ctx];
 
     // ---------------- general path: in-window candidates (newest first), then the frozen record ----------------
     r.n_general++;
@@ -719,54 +724,65 @@ ZL_HD void v3_rollover(const V3Ctx& c, V3Run& r, int nt) {                // sub
 // the minimum that is serial: one 16-byte decision load, the word-MRU push of the token that ended here, the
 // context's insert counter, and a per-position mark; token words, literal lists and bucket writes are produced
 // from the marks by all threads afterwards (v3_token_of / v3_apply_position).  nt0 = tokens emitted before window k.
+// The common path is straight-line code (selects, no branches) so that its independent strands overlap; the
+// decisions of both possible next positions are loaded speculatively.
 ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
     if (r.tail) return;
-    const V3Table t = v3_table(c, k);
+    V3Win w = v3_window(c, k, r.level, tlevel);
+    const uint4* dec = w.t.dec - k * kV3W;                               // dec[x] for x in the table
     const int lim = c.ilen - kGuard;                                     // probes happen at x < lim (lz.cpp:158)
     const int wend = (k + 1) * kV3W < lim ? (k + 1) * kV3W : lim;
+    const int xmax = (k + 1) * kV3W + 1;                                 // last position the table holds
     int x = r.ip, op = r.op;
     uint32_t prev_lit = (uint32_t) r.prev_lit, skip_push = (uint32_t) r.skip_push;
     uint32_t force = r.level != tlevel ? kF_FORCE : 0u;
-    while (x < wend) {
-        const uint4 d = t.dec[x - k * kV3W];
-        {   // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
-            const uint32_t c3 = d.z & 0xffu, w = d.z >> 8;
-            const uint32_t m = c.mru[c3];
-            if (!skip_push && (prev_lit || (m & 0xffffu) != w)) c.mru[c3] = w | (m << 16);
-            skip_push = 0;
-        }
-        if (op + 1 >= kSubSymbols) {
+    if (x >= wend) { if (x >= lim) r.tail = 1; return; }
+    uint4 d = dec[x];
+    while (true) {
+        const uint32_t c3 = d.z & 0xffu, pw = d.z >> 8, ctx = d.y >> 24;
+        const uint32_t m = c.mru[c3];
+        const uint32_t cn = c.cnt[ctx] + 1u;
+        uint32_t flen = d.x & 511u;
+        // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
+        if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) c.mru[c3] = pw | (m << 16);
+        skip_push = 0;
+        if (op + 1 >= kSubSymbols) {                                     // rare: the sub-block is full
             r.ip = x; r.op = op;
             v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));
             op = 0;
             force = r.level != tlevel ? kF_FORCE : 0u;
+            w = v3_window(c, k, r.level, tlevel);
         }
-        const uint32_t ctx = d.y >> 24;
-        uint32_t mark;
-        uint32_t flen = d.x & 511u;
-        if (((d.y & kF_ANY) | force) == 0) {                             // clean: the frozen decision stands
-            const uint32_t cn = c.cnt[ctx] + 1u;
-            c.cnt[ctx] = cn;
-            mark = cn & (kRing - 1);
-        } else {
+        uint32_t mark = cn & (kRing - 1);
+        if (((d.y & kF_ANY) | force) != 0) {                             // flagged: most flags turn out not to hold
             r.n_flagged++;
 #if defined(ZL_V3_FLAG_HIST) && !defined(__CUDA_ARCH__)
             g_flag_hist[((d.y >> 16) & 0x7fu) | (force ? 0x80u : 0u)]++;
 #endif
-            uint32_t midx = 0;
-            flen = (uint32_t) v3_probe(c, r, k, x, tlevel, d, &midx);
-            mark = c.ins[x & (kV3R - 1)] & (kRing - 1 | kInsExplicit);
-            if (flen) c.tw[x & (kV3R - 1)] = tok_match(flen, midx);
+            if (force || v3_hazard(c, w, x, d, cn)) {
+                uint32_t midx = 0;
+                flen = (uint32_t) v3_probe_general(c, r, w, x, d, &midx);
+                mark |= kInsExplicit;
+                if (flen) c.tw[x & (kV3R - 1)] = tok_match(flen, midx);
+            } else {
+                c.cnt[ctx] = cn;
+            }
+        } else {
+            c.cnt[ctx] = cn;
         }
-        if (flen) {
-            c.ins[x & (kV3R - 1)] = mark | (kKindMatch << 12);
-            op += 2; x += (int) flen; prev_lit = 0;
-            continue;
-        }
-        const uint32_t w1 = d.w, m1 = c.mru[ctx];                        // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
-        if ((m1 & 0xffffu) == w1) { c.ins[x & (kV3R - 1)] = mark | (kKindWord0 << 12); op++; x += 2; prev_lit = 0; }
-        else if ((m1 >> 16) == w1) { c.ins[x & (kV3R - 1)] = mark | (kKindWord1 << 12); op++; x += 2; prev_lit = 0; }   // its MRU update = the push at x + 2
-        else { c.ins[x & (kV3R - 1)] = mark | (kKindLit << 12); op++; x += 1; prev_lit = 1; }
+        // next position: x + flen after a match, else x + 2 after a word hit, x + 1 after a literal
+        const int xa = x + (flen ? (int) flen : 1), xb = x + 2;
+        const uint4 dA = dec[xa < xmax ? xa : xmax], dB = dec[xb];
+        const uint32_t m1 = c.mru[ctx];                                  // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
+        const bool w0 = (m1 & 0xffffu) == d.w, w1 = (m1 >> 16) == d.w;
+        const bool word = !flen && (w0 || w1);
+        const uint32_t kind = flen ? kKindMatch : (w0 ? kKindWord0 : (w1 ? kKindWord1 : kKindLit));
+        c.ins[x & (kV3R - 1)] = mark | (kind << 12);
+        prev_lit = kind == kKindLit;
+        op += flen ? 2 : 1;
+        x = word ? xb : xa;
+        d = word ? dB : dA;
+        if (x >= wend) break;
     }
     r.ip = x; r.op = op; r.prev_lit = (int) prev_lit; r.skip_push = (int) skip_push;
     if (x >= lim) r.tail = 1;

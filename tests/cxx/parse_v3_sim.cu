@@ -146,7 +146,8 @@ int main(int argc, char** argv) {
     if (bad < 0 && ((long long) t != sim_nt || j != nsub)) { fprintf(stderr, "count mismatch: sim %d tokens %d subs, oracle %zu tokens %d subs\n", sim_nt, nsub, t, j); bad = 0; }
     zo_rolz_free(z);
     printf("%s level %d order %d: %d bytes, %d tokens, %d sub-blocks, flagged %llu (%.2f%%), general %llu (%.2f%%), slow %llu, linkwalk %llu -> %s\n", argv[1], level, order, ilen,
-           sim_nt, nsub, r.n_flagged, 100.0 * r.n_flagged / (sim_nt ? sim_nt : 1), r.n_general, 100.0 * r.n_general / (sim_nt ? sim_nt : 1), r.n_slow, r.n_linkwalk,
+           sim_nt, nsub, (unsigned long long) r.n_flagged, 100.0 * r.n_flagged / (sim_nt ? sim_nt : 1), (unsigned long long) r.n_general, 100.0 * r.n_general / (sim_nt ? sim_nt : 1),
+           (unsigned long long) r.n_slow, (unsigned long long) r.n_linkwalk,
            bad < 0 ? "OK" : "MISMATCH");
 #if defined(ZL_V3_FLAG_HIST)
     for (int i = 0; i < 256; i++) if (g_flag_hist[i]) printf("  flags %02x: %llu\n", i, g_flag_hist[i]);
