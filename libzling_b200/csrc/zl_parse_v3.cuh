@@ -4,7 +4,7 @@
 // chain per block.  v2 (zl_parse_v2.cuh) alternated "speculate a window" / "resolve a window"; its resolver spent
 // ~1300 cycles per token on warp-wide hazard scans.  v3 keeps v2's exactness argument and changes the schedule:
 //
-//   producers (16 warps)   SPEC(k+1): for every position of window k+1 walk its hash chain in the bucket state G
+//   producers (12 warps)   SPEC(k+1): for every position of window k+1 walk its hash chain in the bucket state G
 //                          frozen at the START OF WINDOW k (G is only written between steps, see APPLY), record
 //                          up to dmax nodes with match lengths, byte-equality maps for the lazy probes, the link
 //                          to the nearest earlier position with the same (context, hash slot) key, and the
@@ -17,7 +17,7 @@
 //                          candidates with the record in the reference's visiting order; (b) replays the
 //                          reference's walk literally on G + the pending inserts.
 //   all threads            APPLY(k): scatter the inserts of window k into G (ring entry + slot head), snapshot the
-//                          per-context insert counters.  Two __syncthreads per window.
+//                          per-context insert counters; token words / literal lists are emitted from the marks here.
 //
 // SPEC(k+1) and RESOLVE(k) touch disjoint state, so they run concurrently; every function of the algorithm is
 // plain scalar code marked ZL_HD, and tests/cxx/parse_v3_sim.cu replays the same phases on the host against the
@@ -27,8 +27,10 @@
 
 namespace zl {
 
-constexpr int kV3Prod    = 480;                 // producer threads (15 warps; 16 warps per CTA keep 128 registers per thread)
-constexpr int kV3Threads = kV3Prod + 32;        // + the resolver warp (warp 0)
+constexpr int kV3Prod    = 384;                 // producer threads: the 12 warps of SM sub-partitions 1..3
+constexpr int kV3Threads = 512;                 // 16 warps (128 registers per thread); warp 0 = resolver, alone on sub-partition 0:
+                                                // warps 4, 8, 12 only help in the short APPLY/EMIT phases, so the resolver keeps its
+                                                // scheduler and instruction cache to itself
 constexpr int kV3W       = kV3Prod - 2;         // main positions per window; each table also holds 2 lazy look-ahead positions
 constexpr int kV3R       = 2048;                // per-position ring (bytes, keys, links, insert marks): >= 3 W + 320
 constexpr int kV3Buckets = 4096;                // bucket table of the link builder
@@ -746,7 +748,7 @@ ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt
         // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
         if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) c.mru[c3] = pw | (m << 16);
         skip_push = 0;
-        if (op + 1 >= kSubSymbols) {                                     // rare: the sub-block is full
+        if (__builtin_expect(op + 1 >= kSubSymbols, 0)) {                // rare: the sub-block is full
             r.ip = x; r.op = op;
             v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));
             op = 0;
@@ -754,7 +756,7 @@ ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt
             w = v3_window(c, k, r.level, tlevel);
         }
         uint32_t mark = cn & (kRing - 1);
-        if (((d.y & kF_ANY) | force) != 0) {                             // flagged: most flags turn out not to hold
+        if (__builtin_expect(((d.y & kF_ANY) | force) != 0, 0)) {        // flagged: most flags turn out not to hold
             r.n_flagged++;
 #if defined(ZL_V3_FLAG_HIST) && !defined(__CUDA_ARCH__)
             g_flag_hist[((d.y >> 16) & 0x7fu) | (force ? 0x80u : 0u)]++;
@@ -823,7 +825,7 @@ struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows,
 
 __device__ __forceinline__ void v3_bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kV3Prod) : "memory"); }
 
-// ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps 1..15 = producers --------
+// ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps w with w % 4 != 0 = producers
 __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, V3Counters* counters) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
@@ -837,8 +839,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
     c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock;
     const int ilen = c.ilen;
-    const bool producer = tid >= 32;
-    const int ptid = tid - 32;
+    const bool producer = (warp & 3) != 0;                               // a warp runs on sub-partition warp % 4
+    const int ptid = (warp - 1 - (warp >> 2)) * 32 + lane;               // 0 .. kV3Prod-1 over the producer warps
 
     for (int i = tid; i < 256; i += kV3Threads) { c.cnt[i] = 0; c.mru[i] = 0; c.snap[i] = 0; c.snap[256 + i] = 0; c.snap[512 + i] = 0; c.pcnt[i] = 0; c.pcnt[256 + i] = 0; }
     for (int i = tid; i < kV3Buckets; i += kV3Threads) c.last[i] = 0;
@@ -952,7 +954,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
             atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));
         }
     }
-    if (tid == 32 && counters) atomicAdd(&counters->cyc_spec, (unsigned long long) cyc_spec);
+    if (tid == 33 && counters) atomicAdd(&counters->cyc_spec, (unsigned long long) cyc_spec);
 }
 #endif
 
