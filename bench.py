@@ -43,6 +43,19 @@ def load_peaks():
     return PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(nbytes, level):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the parse kernel from the committed ncu --set full capture
+    (profiles/r1_parse_traffic.json), valid for the workload it was captured on only; None otherwise"""
+    p = os.path.join(ROOT, "profiles", "r1_parse_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            t = json.load(f)
+        if int(t.get("workload_bytes", -1)) == int(nbytes) and int(t.get("level", -1)) == int(level):
+            return {"GB_per_launch": round((t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e9, 4), "algorithmic_GB_per_launch": round(nbytes / 1e9, 4),
+                    "source": t.get("source")}
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
 
@@ -89,27 +102,48 @@ def cpu_reference(data, level, want_bytes=True):
     return time.perf_counter() - t, z, kind
 
 
-def run_reference(args, data, rank, world):
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU encoder on the host cores, same workload as our arm at N GPUs —
+    N independent streams, one thread each (the reference codec has no threading inside a stream)."""
     if rank != 0:
         return
-    nbytes = data.size
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_reference(data[: min(nbytes, 8 << 20)], args.level)
-    times = []
-    z = b""
-    for _ in range(args.steps):
-        dt, z, kind = cpu_reference(data, args.level)
-        times.append(dt)
+    from libzling_b200 import corpus
+    nbytes = int(args.size_mb * 1e6)
+    streams = [corpus.enwik8_shaped(nbytes, seed=8 + r) if args.corpus == "enwik8" else corpus.mixed(nbytes, seed=4 + r) for r in range(world)]
+    threads_used = min(world, os.cpu_count() or 1)
+    out = [None] * world
+    kinds = []
+
+    def work(i):
+        dt, z, kind = cpu_reference(streams[i], args.level)
+        out[i] = len(z)
+        kinds.append(kind)
+
+    def step():
+        t0 = time.perf_counter()
+        for lo in range(0, world, threads_used):
+            th = [threading.Thread(target=work, args=(i,)) for i in range(lo, min(world, lo + threads_used))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        return time.perf_counter() - t0
+
+    cpu_reference(streams[0][: min(nbytes, 8 << 20)], args.level)          # page the library in
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(args.steps)]
     dt = float(np.mean(times))
-    mbs = nbytes / 1e6 / dt
+    mbs = world * nbytes / 1e6 / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": round(mbs, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "enwik8-shaped %d B, level e%d, CPU reference encoder (single stream)" % (nbytes, args.level),
-                   "bytes": int(nbytes), "level": args.level, "compressed_bytes": len(z)},
-        "cpu_baseline": {"value": round(mbs, 3), "unit": "MB/s", "cores": 1, "kind": kind,
-                         "sample": "whole workload, %d step(s); the reference codec is single-threaded per stream (%d host cores present)" % (args.steps, os.cpu_count())},
+        "config": {"workload": "enwik8-shaped %d B, level e%d, encode, one stream per GPU (BASELINE.json configs[1])" % (nbytes, args.level),
+                   "bytes_per_gpu": int(nbytes), "level": args.level, "streams": world, "compressed_bytes": int(out[0])},
+        "cpu_baseline": {"value": round(mbs, 3), "unit": "MB/s", "cores": threads_used, "kind": kinds[0] if kinds else "reference",
+                         "sample": "the whole workload (%d stream(s) of %d B), %d step(s), one thread per stream; %d host cores present"
+                                   % (world, nbytes, args.steps, os.cpu_count())},
         "e2e": {"value": round(mbs, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -124,6 +158,7 @@ def main():
     ap.add_argument("--size-mb", type=float, default=100.0)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--corpus", default="enwik8", choices=["enwik8", "mixed"], help="mixed = BASELINE.json configs[3] (text + binary + random)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -131,12 +166,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     nbytes = int(args.size_mb * 1e6)
 
-    from libzling_b200 import corpus
-    data = corpus.enwik8_shaped(nbytes, seed=8 + (rank if args.impl == "ours" else 0))
-
     if args.impl == "reference":
-        run_reference(args, data, rank, world)
+        run_reference(args, rank, world)
         return
+    from libzling_b200 import corpus
+    data = corpus.enwik8_shaped(nbytes, seed=8 + rank) if args.corpus == "enwik8" else corpus.mixed(nbytes, seed=4 + rank)
 
     import torch
     import libzling_b200
@@ -213,25 +247,51 @@ def main():
     for _ in range(max(1, args.warmup - 2)):
         step_host()
     e2e_s = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        t = time.perf_counter()
         n, st_h = step_host()
-        if dist is not None:     # single gather of the packed outputs over NCCL (sizes, then padded payloads)
+        ms = st_h["ms_total"]            # engine events on its own stream: H2D -> kernels -> D2H of the framed stream
+        if dist is not None:             # single gather of the packed outputs over NCCL (sizes, then padded payloads)
+            ev0.record()
             sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device="cuda"))
-            mx = int(max(int(s.item()) for s in sizes))
+            mx = int(max(int(x.item()) for x in sizes))
             mine = torch.zeros(mx, dtype=torch.uint8, device="cuda")
             mine[:n].copy_(torch.from_numpy(pin_out.array[:n]))
             bufs = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
             dist.gather(mine, bufs, dst=0)
+            ev1.record()
             torch.cuda.synchronize()
-        e2e_s.append(time.perf_counter() - t)
+            ms += ev0.elapsed_time(ev1)
+        e2e_s.append(ms / 1e3)
         assert n == len(want)
     barrier()
     clocks = sampler.stop()
+
+    # ---- secondary: decode (BASELINE.json configs[4] shape) on a bounded sample — the first 16 MiB block of the stream.
+    # One chain per stream (MTF state + context dependence): reported, not optimised for, next to the CPU decoder.
+    decode = None
+    if rank == 0:
+        from _libs import Ref, Oracle, have_ref, bound  # noqa: F401
+        sample = data[: min(nbytes, libzling_b200.BLOCK)]
+        zs = ctx.encode(sample, args.level)
+        back = ctx.decode(zs)                                             # warm-up + round-trip check
+        if back != sample.tobytes():
+            raise SystemExit("bench.py: GPU decode round trip failed")
+        dts = []
+        for _ in range(2):
+            ctx.decode(zs)
+            dts.append(ctx.stats()["ms_total"])
+        lib = Ref() if have_ref() else Oracle()
+        t0 = time.perf_counter()
+        lib.decode(zs, sample.size)
+        cpu_dec = time.perf_counter() - t0
+        decode = {"value": round(sample.size / 1e6 / (min(dts) / 1e3), 3), "unit": "MB/s (decoded bytes)", "sample": "first %d B of the stream, 1 block" % sample.size,
+                  "ms": round(min(dts), 3), "cpu_reference_mbs": round(sample.size / 1e6 / cpu_dec, 3),
+                  "note": "single-stream decode is one serial chain (DESIGN.md 4.5)"}
     assert bytes(pin_out.array[:n]) == want or args.skip_parity
 
     ms_step = float(np.mean(dev_ms))
@@ -250,7 +310,8 @@ def main():
             "metric": METRIC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": "enwik8-shaped %d B, level e%d, encode, one stream per GPU (BASELINE.json configs[1])" % (nbytes, args.level),
+            "config": {"workload": "%s %d B, level e%d, encode, one stream per GPU%s" % ("enwik8-shaped" if args.corpus == "enwik8" else "mixed text+binary+random", nbytes, args.level,
+                                                                                          " (BASELINE.json configs[1])" if (args.corpus, nbytes, args.level) == ("enwik8", 100000000, 0) else ""),
                        "bytes_per_gpu": int(nbytes), "level": args.level, "blocks_per_gpu": int(nblocks), "compressed_bytes": len(want),
                        "ratio": round(ratio, 4), "bit_exact_vs_cpu_reference": not args.skip_parity,
                        "l2": "256 MB buffer written between timed steps (L2 flush); working set (input + 12 MB bucket state/block + tokens) exceeds L2",
@@ -260,7 +321,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "zl_rolz_parse_v%s (one launch per step, 1 CTA per 16 MiB block)" % os.environ.get("ZLB_PARSE", "3"),
-                         "achieved": round(ach, 4), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": None,
+                         "achieved": round(ach, 4), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": load_traffic(nbytes, args.level),
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (each read once); the kernel is bound by the serial token chain, not HBM "
                                  "(DESIGN.md §4): %d tokens in %d chains" % (last["tokens"], nblocks)},
@@ -268,6 +329,7 @@ def main():
                           "pack": round(float(np.mean(pack_ms)), 3), "wall_ms_per_step_incl_flush": round(wall_dev / args.steps * 1e3, 3)},
             "parse_counters": {k: int(last[k]) for k in ("tokens", "subblocks", "slow_main", "slow_lazy", "general_path", "window_hits", "windows", "reparsed_blocks",
                                                           "cyc_spec", "cyc_resolve", "cyc_total", "flagged")},
+            "decode": decode,
             "cpu_baseline": {"value": round(nbytes / 1e6 / cpu_dt, 3), "unit": "MB/s", "cores": 1, "kind": cpu_kind,
                              "sample": "the whole %d-byte workload once, single thread (the reference codec has no threading); %d host cores present" % (nbytes, os.cpu_count())},
         }

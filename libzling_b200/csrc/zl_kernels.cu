@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
     __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
     __shared__ __align__(16) uint8_t s_out[kMtfChunk];
+    __shared__ __align__(16) uint8_t s_next[256];         // mtf_next() as a table: one load instead of a multiply-divide chain
+    for (int i = lane; i < 256; i += 32) s_next[i] = (uint8_t) mtf_next(i);
     {
         const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
         for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
@@ -437,12 +439,12 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
                 for (; q + 1 < cnt; q += 2) {
                     const uint32_t bA = s_rec[buf][q] & 0xffu, bB = s_rec[buf][q + 1] & 0xffu;
                     const int iA = s_rank[bA], iBr = s_rank[bB];
-                    const int jA = mtf_next(iA);
+                    const int jA = s_next[iA];
                     int iB = bB == bA ? jA : iBr;                       // assumes bB is not the byte A swaps with
-                    int jB = mtf_next(iB);
+                    int jB = s_next[iB];
                     const uint32_t oA = s_sym[jA];
                     uint32_t oBr = s_sym[jB];
-                    if (bB == oA && bB != bA) { iB = iA; jB = mtf_next(iB); oBr = s_sym[jB]; }
+                    if (bB == oA && bB != bA) { iB = iA; jB = s_next[iB]; oBr = s_sym[jB]; }
                     const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);
                     s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;
                     s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
                 }
                 for (; q < cnt; q++) {
                     const uint32_t byte = s_rec[buf][q] & 0xffu;
-                    const int i = s_rank[byte], jn = mtf_next(i);
+                    const int i = s_rank[byte], jn = s_next[i];
                     const uint32_t other = s_sym[jn];
                     s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;
                     s_rank[other] = (uint8_t) i; s_rank[byte] = (uint8_t) jn;

@@ -748,6 +748,16 @@ ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt
         // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
         if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) c.mru[c3] = pw | (m << 16);
         skip_push = 0;
+        const bool special = ((d.y & kF_ANY) | force) != 0 || op + 1 >= kSubSymbols;
+        if (!special && flen) {                                          // clean match (55 % of the tokens): the short way round
+            const int xn = x + (int) flen;
+            const uint4 dn = dec[xn < xmax ? xn : xmax];
+            c.cnt[ctx] = cn;
+            c.ins[x & (kV3R - 1)] = (cn & (kRing - 1)) | (kKindMatch << 12);
+            op += 2; prev_lit = 0; x = xn; d = dn;
+            if (x >= wend) break;
+            continue;
+        }
         if (__builtin_expect(op + 1 >= kSubSymbols, 0)) {                // rare: the sub-block is full
             r.ip = x; r.op = op;
             v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));

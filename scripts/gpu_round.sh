@@ -11,7 +11,13 @@ timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 
 tail -5 gpurun_out/${TAG}_pytest.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
-if [ "$2" != "quick" ]; then
+if [ "$2" == "big" ]; then
+  timeout 900 python bench.py --steps 2 --warmup 3 --size-mb 1000 --level 2 --corpus mixed > gpurun_out/${TAG}_bench_1g_e2.json 2> gpurun_out/${TAG}_bench_1g_e2.err; echo "bench 1g rc=$?"
+  cat gpurun_out/${TAG}_bench_1g_e2.json | cut -c1-1500; tail -3 gpurun_out/${TAG}_bench_1g_e2.err
+  timeout 600 python bench.py --steps 2 --warmup 3 --level 4 > gpurun_out/${TAG}_bench_e4.json 2> gpurun_out/${TAG}_bench_e4.err; echo "bench e4 rc=$?"
+  cat gpurun_out/${TAG}_bench_e4.json | cut -c1-1500; tail -3 gpurun_out/${TAG}_bench_e4.err
+fi
+if [ "$2" == "full" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:zl_rolz_parse_v3 -c 1 -o gpurun_out/${TAG}_parse_v3 -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full.log 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:zl_mtf_ctx -c 1 -o gpurun_out/${TAG}_mtf_ctx -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full2.log 2>&1
