@@ -257,7 +257,8 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         for (int b = 0; b < nb; b++) {
             c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
             c->h_active[b] = 1;
-            memset(c->h_plan + (size_t) b * kMaxSubPerBlock, e->level, kMaxSubPerBlock);
+            // v3 predicts the level of a sub-block from the previous one (kPlanAuto); v1/v2 get explicit levels
+            memset(c->h_plan + (size_t) b * kMaxSubPerBlock, c->parse_version == 3 ? (int) kPlanAuto : e->level, kMaxSubPerBlock);
         }
         c->h_plan[0] = (uint8_t) e->cur_level;                    // current_level outlives blocks, libzling.cpp:185
         CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
@@ -289,7 +290,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V3Layout lay = v3_layout(dmax, lmax);
             if (pass == 0) CU(cudaMemsetAsync(c->d_v3c, 0, sizeof(V3Counters), st));
-            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, c->d_v3c);
+            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, e->level, c->d_v3c);
         } else {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const int W = e->level <= 2 ? 1024 : 512;
@@ -327,41 +328,46 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
           cudaEventElapsedTime(&t, c->ev[EV_PARSE1], c->ev[EV_MTF1]); ms_mtf += t;
           cudaEventElapsedTime(&t, c->ev[EV_MTF1], c->ev[EV_BUILD1]); ms_build += t; }
 
-        // verify the plan in stream order (libzling.cpp:261-266)
-        int cur = e->cur_level, bad_b = -1, bad_j = -1;
-        for (int b = 0; b < nb && bad_b < 0; b++) {
+        // Verify the levels in stream order (libzling.cpp:261-266) and re-plan EVERY block that used a wrong one in
+        // this pass: sub-blocks before the first wrong one are pinned to their (verified) levels, the wrong one gets
+        // the level the reference uses, later ones are predicted again by the parse.  Behind a wrong block the
+        // walk continues on the assumption that the compressibility of its last sub-block does not change with the
+        // level (incompressible data stays incompressible), so all mispredicted blocks of a call are usually
+        // re-parsed together, concurrently, in ONE extra pass.  A wrong assumption only costs another pass.
+        int cur = e->cur_level, nbad = 0, first_bad = -1;
+        bool exact = true;                                            // `cur` is the reference's value, not an assumption
+        for (int b = 0; b < nb; b++) {
             const int ns = (int) c->h_nsub[b];
             if (ns > kMaxSubPerBlock) return fail(ZLB_E_CUDA, "internal: sub-block table overflow");
+            c->h_active[b] = 0;
+            uint8_t* plan = c->h_plan + (size_t) b * kMaxSubPerBlock;
+            int bad_j = -1;
             for (int j = 0; j < ns; j++) {
-                const SubBlock& s = c->h_sub[(size_t) b * kMaxSubPerBlock + j];
-                if ((int) s.level != cur) { bad_b = b; bad_j = j; break; }
-                cur = incompressible(s) ? 0 : e->level;
+                const SubBlock& sb = c->h_sub[(size_t) b * kMaxSubPerBlock + j];
+                if (bad_j < 0 && (int) sb.level != cur) {
+                    bad_j = j;
+                    plan[j] = (uint8_t) cur;
+                    for (int q = j + 1; q < kMaxSubPerBlock; q++) plan[q] = c->parse_version == 3 ? (uint8_t) kPlanAuto : (uint8_t) e->level;
+                    if (c->parse_version != 3) {                      // v1/v2 cannot predict: guess from how the wrong run compressed
+                        for (int q = j + 1; q < kMaxSubPerBlock; q++) {
+                            const bool prev_bad = q - 1 < ns && incompressible(c->h_sub[(size_t) b * kMaxSubPerBlock + q - 1]);
+                            plan[q] = prev_bad ? 0 : (uint8_t) e->level;
+                        }
+                    }
+                } else if (bad_j < 0 && exact) {
+                    plan[j] = (uint8_t) sb.level;                     // verified: pin it for any later re-parse of this block
+                }
+                cur = incompressible(sb) ? 0 : e->level;
+            }
+            if (bad_j >= 0) {
+                c->h_active[b] = 1; nbad++; reparsed++;
+                if (first_bad < 0) first_bad = b;
+                exact = false;                                        // everything behind rests on an assumption
             }
         }
-        if (bad_b < 0) { final_level = cur; break; }
+        if (nbad == 0) { final_level = cur; break; }
         if (pass > nb * kMaxSubPerBlock + 4) return fail(ZLB_E_CUDA, "internal: level-feedback replay did not converge");
-        // Re-plan block bad_b: sub-blocks before bad_j are verified; bad_j gets the level the reference would
-        // use; later ones are predicted from how compressible the same index was in the wrong run (incompressible
-        // data stays incompressible at any level).  A wrong guess only costs another pass, never correctness.
-        uint8_t* plan = c->h_plan + (size_t) bad_b * kMaxSubPerBlock;
-        const int ns = (int) c->h_nsub[bad_b];
-        plan[bad_j] = (uint8_t) cur;
-        for (int j = bad_j + 1; j < kMaxSubPerBlock; j++) {
-            const bool prev_bad = j - 1 < ns && incompressible(c->h_sub[(size_t) bad_b * kMaxSubPerBlock + j - 1]);
-            plan[j] = prev_bad ? 0 : (uint8_t) e->level;
-        }
-        // first sub-block of the next block follows the last sub-block of this one (prediction)
-        if (bad_b + 1 < nb && ns > 0) {
-            const bool last_bad = incompressible(c->h_sub[(size_t) bad_b * kMaxSubPerBlock + ns - 1]);
-            const uint8_t want = last_bad ? 0 : (uint8_t) e->level;
-            uint8_t* nplan = c->h_plan + (size_t) (bad_b + 1) * kMaxSubPerBlock;
-            for (int b = 0; b < nb; b++) c->h_active[b] = 0;
-            if (nplan[0] != want) { nplan[0] = want; c->h_active[bad_b + 1] = 1; reparsed++; }
-        } else {
-            for (int b = 0; b < nb; b++) c->h_active[b] = 0;
-        }
-        c->h_active[bad_b] = 1; reparsed++;
-        first_dirty = bad_b;
+        first_dirty = first_bad;
     }
 
     // layout of the framed stream: per sub-block 1 + 12 + olen bytes, one stop byte per block

@@ -144,7 +144,7 @@ struct V3Ctx {
     // block
     const uint8_t* in; int ilen;
     uint64_t* ring; uint16_t* hash;             // G: bucket state in global memory
-    uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan;
+    uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory
     uint32_t* rbw;                              // input bytes, ring of kV3R bytes viewed as words
     uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* ins; uint16_t* suf; uint32_t* tw;
@@ -714,10 +714,24 @@ ZL_HD void v3_close_subblock(const V3Ctx& c, V3Run& r, int nt) {
         c.sub[r.j] = sb;
     }
 }
+// Level of sub-block j.  The reference derives it from the PREVIOUS sub-block's Huffman size (src/libzling.cpp:261-266:
+// olen / (consumed + 1) > 0.95 => level 0), which is not known during the parse (the literal ranks depend on MTF state
+// carried across blocks).  plan[j] is the host's word: a level it has verified, or kPlanAuto = "predict": a sub-block
+// that is almost all single-byte symbols (consumed <= 1.125 x symbols) will not compress.  The host verifies every
+// level afterwards from the real sizes and re-parses from the first wrong one, so a wrong guess only costs time.
+constexpr uint32_t kPlanAuto = 0xffu;
+ZL_HD int v3_next_level(const V3Ctx& c, const V3Run& r, int j) {
+    const uint32_t p = c.plan[j < kMaxSubPerBlock ? j : kMaxSubPerBlock - 1];
+    if (p != kPlanAuto) return (int) p;
+    if (j == 0) return c.base_level;
+    const int consumed = r.ip - r.enc_begin;
+    return consumed <= r.op + (r.op >> 3) ? 0 : c.base_level;
+}
 ZL_HD void v3_rollover(const V3Ctx& c, V3Run& r, int nt) {                // sub-block full (lz.cpp:153): close it, open the next
     v3_close_subblock(c, r, nt);
+    const int next = v3_next_level(c, r, r.j + 1);
     r.j++;
-    r.level = c.plan[r.j < kMaxSubPerBlock ? r.j : kMaxSubPerBlock - 1];
+    r.level = next;
     for (int i = 0; i < 256; i++) c.mru[i] = 0;                          // lz.cpp:147
     r.op = 0; r.tok_begin = nt; r.enc_begin = r.ip;
 }
@@ -836,7 +850,7 @@ struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows,
 __device__ __forceinline__ void v3_bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kV3Prod) : "memory"); }
 
 // ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps w with w % 4 != 0 = producers
-__global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, V3Counters* counters) {
+__global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, int base_level, V3Counters* counters) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -847,7 +861,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     c.in = a.in + (size_t) b * kBlockBytes; c.ilen = (int) a.ilen[b];
     c.ring = a.ring + (size_t) b * kRingStride; c.hash = a.hash + (size_t) b * kHashStride;
     c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
-    c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock;
+    c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock; c.base_level = base_level;
     const int ilen = c.ilen;
     const bool producer = (warp & 3) != 0;                               // a warp runs on sub-partition warp % 4
     const int ptid = (warp - 1 - (warp >> 2)) * 32 + lane;               // 0 .. kV3Prod-1 over the producer warps
@@ -857,7 +871,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     for (int i = tid; i < kV3R; i += kV3Threads) { c.ins[i] = 0; c.link[i] = 0; c.blink[i] = 0; c.key[i] = kKeyInvalid; }
 
     V3Run r;
-    r.ip = 0; r.op = 0; r.j = 0; r.level = c.plan[0]; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
+    r.ip = 0; r.op = 0; r.j = 0; r.level = 0; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
+    r.enc_begin = 0; r.level = v3_next_level(c, r, 0);
     r.n_general = 0; r.n_slow = 0; r.n_linkwalk = 0; r.n_flagged = 0;
     long long cyc_res = 0, cyc_spec = 0;
     const long long t_begin = clock64();

@@ -31,7 +31,9 @@ int main(int argc, char** argv) {
     const int order = argc > 3 ? atoi(argv[3]) : 0;
     uint8_t plan[kMaxSubPerBlock];
     memset(plan, level, sizeof plan);
-    if (argc > 4) for (size_t i = 0; i < strlen(argv[4]) && i < (size_t) kMaxSubPerBlock; i++) plan[i] = (uint8_t) (argv[4][i] - '0');
+    // plan digits pin levels per sub-block; 'a' = auto (the kernel predicts), "auto" = every sub-block auto
+    if (argc > 4 && !strcmp(argv[4], "auto")) memset(plan, 0xff, sizeof plan);
+    else if (argc > 4) for (size_t i = 0; i < strlen(argv[4]) && i < (size_t) kMaxSubPerBlock; i++) plan[i] = argv[4][i] == 'a' ? 0xff : (uint8_t) (argv[4][i] - '0');
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror(argv[1]); return 2; }
     std::vector<uint8_t> data;
@@ -56,11 +58,11 @@ int main(int argc, char** argv) {
     V3Ctx c;
     v3_bind(c, smem, L);
     c.in = in; c.ilen = ilen; c.ring = ring.data(); c.hash = hash.data(); c.tok = tok.data(); c.lit = lit.data();
-    c.sub = sub.data(); c.plan = plan;
+    c.sub = sub.data(); c.plan = plan; c.base_level = level;
     for (int i = 0; i < kV3R; i++) c.key[i] = kKeyInvalid;
 
     V3Run r; memset(&r, 0, sizeof r);
-    r.level = plan[0]; r.skip_push = 1;
+    r.level = v3_next_level(c, r, 0); r.skip_push = 1;
     int nt = 0, nl = 0;
     for (int first = 0; first < 2; first++)
         if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(in[r.ip], 0, true); r.op++; r.ip++; }
@@ -115,7 +117,7 @@ int main(int argc, char** argv) {
     size_t t = 0;
     long long bad = -1;
     while (encpos < ilen && bad < 0) {
-        const int lv = plan[j < kMaxSubPerBlock ? j : kMaxSubPerBlock - 1];
+        const int lv = j < nsub ? (int) sub[j].level : level;             // the level the replay used (pinned or predicted)
         zo_rolz_trace(z, tp.data(), tr.data(), (int) tp.size());
         const int enc0 = encpos;
         const int rlen = zo_rolz_encode(z, lv, in, sym.data(), ilen, kSubSymbols, &encpos);
