@@ -63,6 +63,7 @@ struct zlb_ctx {
     zlb_stats stats = {};
     int last_nblocks = 0;
     int parse_version = 3;          // ZLB_PARSE=1: literal one-warp-per-block chain walker, 2: windowed speculate/resolve, 3: pipelined (default)
+    int v3_serialize = 0;           // ZLB_V3_SERIAL=1: experiment, run RESOLVE(k) after SPEC(k+1) instead of concurrently
     int mtf_version = 2;            // ZLB_MTF=1: one warp per stream, 2: one CTA per context (default)
     V2Counters* d_v2c = nullptr;
     V2Counters  h_v2c = {};
@@ -168,6 +169,7 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaFuncSetAttribute(zl_rolz_parse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3_layout(depth_main(4), depth_lazy1(4)).total));
     { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv >= '1' && *pv <= '3') c->parse_version = *pv - '0'; }
+    { const char* pv = getenv("ZLB_V3_SERIAL"); if (pv && *pv == '1') c->v3_serialize = 1; }
     { const char* pv = getenv("ZLB_MTF"); if (pv && *pv >= '1' && *pv <= '2') c->mtf_version = *pv - '0'; }
     CU(cudaFuncSetAttribute(zl_mtf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
@@ -290,7 +292,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V3Layout lay = v3_layout(dmax, lmax);
             if (pass == 0) CU(cudaMemsetAsync(c->d_v3c, 0, sizeof(V3Counters), st));
-            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, e->level, c->d_v3c);
+            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, e->level, c->v3_serialize, c->d_v3c);
         } else {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const int W = e->level <= 2 ? 1024 : 512;

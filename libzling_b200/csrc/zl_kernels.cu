@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
     __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
     __shared__ __align__(16) uint8_t s_out[kMtfChunk];
+    __shared__ __align__(16) uint8_t s_byte[2][kMtfChunk + 16];
     __shared__ __align__(16) uint8_t s_next[256];         // mtf_next() as a table: one load instead of a multiply-divide chain
     for (int i = lane; i < 256; i += 32) s_next[i] = (uint8_t) mtf_next(i);
     {
@@ -425,35 +426,46 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
         for (int q = 0; q < kMtfChunk / 32; q++) { const int i = q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
         for (int base = 0, buf = 0; base < n; base += kMtfChunk, buf ^= 1) {
             #pragma unroll
-            for (int q = 0; q < kMtfChunk / 32; q++) s_rec[buf][q * 32 + lane] = pre[q];
+            for (int q = 0; q < kMtfChunk / 32; q++) { s_rec[buf][q * 32 + lane] = pre[q]; s_byte[buf][q * 32 + lane] = (uint8_t) pre[q]; }
             #pragma unroll
             for (int q = 0; q < kMtfChunk / 32; q++) { const int i = base + kMtfChunk + q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
             __syncwarp();
             const int cnt = min(kMtfChunk, n - base);
             if (lane == 0) {
-                int q = 0;
-                // two literals per step: the second one's table reads are issued together with the first one's and
+                // Two literals per step: the second one's table reads are issued together with the first one's and
                 // patched from registers where the first literal's swap touches them (the swap moves two entries).
-                // Ranks go to shared memory; the token words are written by all lanes after the chunk.
-                #pragma unroll 2
-                for (; q + 1 < cnt; q += 2) {
-                    const uint32_t bA = s_rec[buf][q] & 0xffu, bB = s_rec[buf][q + 1] & 0xffu;
-                    const int iA = s_rank[bA], iBr = s_rank[bB];
-                    const int jA = s_next[iA];
-                    int iB = bB == bA ? jA : iBr;                       // assumes bB is not the byte A swaps with
-                    int jB = s_next[iB];
-                    const uint32_t oA = s_sym[jA];
-                    uint32_t oBr = s_sym[jB];
-                    if (bB == oA && bB != bA) { iB = iA; jB = s_next[iB]; oBr = s_sym[jB]; }
-                    const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);
-                    s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;
-                    s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;
-                    s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;
-                    s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;
-                    s_out[q] = (uint8_t) iA; s_out[q + 1] = (uint8_t) iB;
+                // Bytes come four at a time (prefetched one step ahead), ranks leave four at a time; the token
+                // words are written by all lanes after the chunk.
+                #define ZL_MTF_PAIR(bA, bB, rA, rB) {                                                              \
+                    const int iA = s_rank[bA], iBr = s_rank[bB];                                                  \
+                    const int jA = s_next[iA];                                                                    \
+                    int iB = bB == bA ? jA : iBr;                       /* assumes bB is not the byte A swaps with */ \
+                    int jB = s_next[iB];                                                                          \
+                    const uint32_t oA = s_sym[jA];                                                                \
+                    uint32_t oBr = s_sym[jB];                                                                     \
+                    if (bB == oA && bB != bA) { iB = iA; jB = s_next[iB]; oBr = s_sym[jB]; }                      \
+                    const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);                                    \
+                    s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;                                           \
+                    s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;                                         \
+                    s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;                                           \
+                    s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;                                         \
+                    rA = (uint32_t) iA; rB = (uint32_t) iB; }
+                int q = 0;
+                const uint32_t* byte4 = reinterpret_cast<const uint32_t*>(s_byte[buf]);
+                uint32_t* out4 = reinterpret_cast<uint32_t*>(s_out);
+                uint32_t nb4 = byte4[0];
+                for (; q + 3 < cnt; q += 4) {
+                    const uint32_t b4 = nb4;
+                    nb4 = byte4[(q >> 2) + 1];
+                    const uint32_t b0 = b4 & 0xffu, b1 = (b4 >> 8) & 0xffu, b2 = (b4 >> 16) & 0xffu, b3 = b4 >> 24;
+                    uint32_t r0, r1, r2, r3;
+                    ZL_MTF_PAIR(b0, b1, r0, r1)
+                    ZL_MTF_PAIR(b2, b3, r2, r3)
+                    out4[q >> 2] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
                 }
+                #undef ZL_MTF_PAIR
                 for (; q < cnt; q++) {
-                    const uint32_t byte = s_rec[buf][q] & 0xffu;
+                    const uint32_t byte = s_byte[buf][q];
                     const int i = s_rank[byte], jn = s_next[i];
                     const uint32_t other = s_sym[jn];
                     s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;

@@ -850,7 +850,7 @@ struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows,
 __device__ __forceinline__ void v3_bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kV3Prod) : "memory"); }
 
 // ---- the kernel: grid = blocks of the batch, kV3Threads threads; warp 0 = resolver, warps w with w % 4 != 0 = producers
-__global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, int base_level, V3Counters* counters) {
+__global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseArgs a, int dmax, int lmax, int base_level, int serialize, V3Counters* counters) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -929,7 +929,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
                 if (ptid == 0) s_tlevel[j & 1] = tlevel_next;
                 cyc_spec += clock64() - t0;
             }
-        } else if (tid == 0 && k >= 0) {
+        }
+        if (serialize) __syncthreads();                                  // experiment: RESOLVE(k) after SPEC(k+1) instead of beside it
+        if (tid == 0 && k >= 0) {
             const long long t0 = clock64();
             v3_resolve_window(c, r, k, s_tlevel[k & 1], s_nt);
             cyc_res += clock64() - t0;
