@@ -183,6 +183,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     nblocks = (nbytes + libzling_b200.BLOCK - 1) // libzling_b200.BLOCK
