@@ -751,52 +751,75 @@ ZL_HD void v3_rollover(const V3Ctx& c, V3Run& r, int nt) {                // sub
 constexpr int kV3Batch = 32;
 enum { kWalkEnd = 0, kWalkFull = 1, kWalkSpecial = 2 };
 
-ZL_HD int v3_walk_serial(const V3Ctx& c, V3Run& r, int k, int tlevel, int* n_out) {
-    *n_out = 0;
-    if (r.tail) return kWalkEnd;
-    const uint4* dec = v3_table(c, k).dec - k * kV3W;                    // dec[x] for x in the table
-    const int lim = c.ilen - kGuard;                                     // probes happen at x < lim (lz.cpp:158)
-    const int wend = (k + 1) * kV3W < lim ? (k + 1) * kV3W : lim;
-    const int xmax = (k + 1) * kV3W + 1;                                 // last position the table holds
-    int x = r.ip, op = r.op, n = 0, reason = kWalkEnd;
-    uint32_t prev_lit = (uint32_t) r.prev_lit, skip_push = (uint32_t) r.skip_push;
-    const uint32_t force = r.level != tlevel ? kF_FORCE : 0u;
-    if (x >= wend) { if (x >= lim) r.tail = 1; return kWalkEnd; }
-    uint4 d = dec[x];
+// The hot loop lives in its own non-inlined function so that its instructions are contiguous (the resolver is one
+// thread: it has nobody to hide instruction-fetch latency behind, and the kernel around it is > 150 KB of code).
+// Shared memory is addressed explicitly on the device (32-bit shared-window addresses), by pointer on the host.
+#if defined(__CUDA_ARCH__)
+typedef uint32_t z3_sptr;
+__device__ __forceinline__ z3_sptr z3_sp(const void* p) { return (z3_sptr) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 z3_lds128(z3_sptr a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t z3_lds32(z3_sptr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void z3_sts32(z3_sptr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+#else
+typedef uintptr_t z3_sptr;
+inline z3_sptr z3_sp(const void* p) { return (z3_sptr) p; }
+inline uint4 z3_lds128(z3_sptr a) { return *reinterpret_cast<const uint4*>(a); }
+inline uint32_t z3_lds32(z3_sptr a) { return *reinterpret_cast<const uint32_t*>(a); }
+inline void z3_sts32(z3_sptr a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
+#endif
+struct V3WalkIO { int x, op, n, reason; uint32_t prev_lit, skip_push; };
+
+// dec0 = address of dec[0] (position 0, i.e. table base - k W entries), 16 bytes per position
+__host__ __device__ __noinline__ void v3_walk_core(z3_sptr dec0, z3_sptr mru, z3_sptr bq, int wend, int xmax, uint32_t force, V3WalkIO* io) {
+    int x = io->x, op = io->op, n = 0, reason = kWalkEnd;
+    uint32_t prev_lit = io->prev_lit, skip_push = io->skip_push;
+    uint4 d = z3_lds128(dec0 + (z3_sptr) x * 16u);
     while (true) {
         const uint32_t c3 = d.z & 0xffu, pw = d.z >> 8, ctx = d.y >> 24;
-        const uint32_t m = c.mru[c3];
+        const uint32_t m = z3_lds32(mru + c3 * 4u);
         const uint32_t flen = d.x & 511u;
         // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
-        if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) c.mru[c3] = pw | (m << 16);
+        if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) z3_sts32(mru + c3 * 4u, pw | (m << 16));
         skip_push = 0;
-        if (__builtin_expect((((d.y & kF_ANY) | force) != 0) | (op + 1 >= kSubSymbols), 0)) {
+        if ((((d.y & kF_ANY) | force) != 0) | (op + 1 >= kSubSymbols)) {
             skip_push = 1;                                               // the push for x is done; the special handler must not repeat it
             reason = kWalkSpecial;
             break;
         }
         if (flen) {                                                      // clean match
-            c.bq[n++] = (uint32_t) x | (kKindMatch << 24);
-            op += 2; prev_lit = 0; x += (int) flen;
+            z3_sts32(bq + (z3_sptr) n * 4u, (uint32_t) x | (kKindMatch << 24));
+            n++; op += 2; prev_lit = 0; x += (int) flen;
             if (x >= wend) break;
-            d = dec[x < xmax ? x : xmax];
+            d = z3_lds128(dec0 + (z3_sptr) (x < xmax ? x : xmax) * 16u);
         } else {                                                         // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
-            const uint4 dA = dec[x + 1], dB = dec[x + 2];
-            const uint32_t m1 = c.mru[ctx];
+            const uint4 dA = z3_lds128(dec0 + (z3_sptr) (x + 1) * 16u), dB = z3_lds128(dec0 + (z3_sptr) (x + 2) * 16u);
+            const uint32_t m1 = z3_lds32(mru + ctx * 4u);
             const bool w0 = (m1 & 0xffffu) == d.w, w1 = (m1 >> 16) == d.w;
             const uint32_t kind = w0 ? kKindWord0 : (w1 ? kKindWord1 : kKindLit);
-            c.bq[n++] = (uint32_t) x | (kind << 24);
-            op += 1; prev_lit = kind == kKindLit;
+            z3_sts32(bq + (z3_sptr) n * 4u, (uint32_t) x | (kind << 24));
+            n++; op += 1; prev_lit = kind == kKindLit;
             x += (w0 || w1) ? 2 : 1;                                     // a word-257 hit's MRU update is the push made on arrival at x + 2
             d = (w0 || w1) ? dB : dA;
             if (x >= wend) break;
         }
         if (n == kV3Batch) { reason = kWalkFull; break; }
     }
-    r.ip = x; r.op = op; r.prev_lit = (int) prev_lit; r.skip_push = (int) skip_push;
-    if (reason != kWalkSpecial && x >= lim) r.tail = 1;
-    *n_out = n;
-    return reason;
+    io->x = x; io->op = op; io->n = n; io->reason = reason; io->prev_lit = prev_lit; io->skip_push = skip_push;
+}
+
+ZL_HD int v3_walk_serial(const V3Ctx& c, V3Run& r, int k, int tlevel, int* n_out, V3WalkIO* io) {
+    *n_out = 0;
+    if (r.tail) return kWalkEnd;
+    const int lim = c.ilen - kGuard;                                     // probes happen at x < lim (lz.cpp:158)
+    const int wend = (k + 1) * kV3W < lim ? (k + 1) * kV3W : lim;
+    const int xmax = (k + 1) * kV3W + 1;                                 // last position the table holds
+    if (r.ip >= wend) { if (r.ip >= lim) r.tail = 1; return kWalkEnd; }
+    io->x = r.ip; io->op = r.op; io->prev_lit = (uint32_t) r.prev_lit; io->skip_push = (uint32_t) r.skip_push;
+    v3_walk_core(z3_sp(v3_table(c, k).dec) - (z3_sptr) (k * kV3W) * 16u, z3_sp(c.mru), z3_sp(c.bq), wend, xmax, r.level != tlevel ? kF_FORCE : 0u, io);
+    r.ip = io->x; r.op = io->op; r.prev_lit = (int) io->prev_lit; r.skip_push = (int) io->skip_push;
+    if (io->reason != kWalkSpecial && r.ip >= lim) r.tail = 1;
+    *n_out = io->n;
+    return io->reason;
 }
 
 // bookkeeping of one queued token (host replay and reference form of the warp-wide flush in the kernel)
@@ -809,7 +832,7 @@ ZL_HD void v3_batch_apply_one(const V3Ctx& c, uint32_t e) {
 }
 
 // the token at r.ip whose decision is flagged / whose sub-block is full; its word-MRU push has been made already
-ZL_HD void v3_token_special(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
+ZL_HD void v3_token_special(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {   // (inlined: it needs the whole context)
     const int x = r.ip;
     const uint4 d = v3_table(c, k).dec[x - k * kV3W];
     const int lim = c.ilen - kGuard;
@@ -850,9 +873,10 @@ ZL_HD void v3_token_special(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0
 
 // host form of RESOLVE(k) (the kernel runs the same three pieces with the flush spread over the resolver warp)
 inline void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
+    V3WalkIO io;
     while (true) {
         int n = 0;
-        const int reason = v3_walk_serial(c, r, k, tlevel, &n);
+        const int reason = v3_walk_serial(c, r, k, tlevel, &n, &io);
         for (int t = 0; t < n; t++) v3_batch_apply_one(c, c.bq[t]);
         if (reason == kWalkSpecial) v3_token_special(c, r, k, tlevel, nt0);
         else if (reason == kWalkEnd) break;
@@ -900,6 +924,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int s_level, s_tlevel[2], s_nt, s_nl, s_wtok[kV3Threads / 32], s_wlit[kV3Threads / 32];
+    __shared__ V3WalkIO s_io;
     const V3Layout L = v3_layout(dmax, lmax);
     V3Ctx c;
     v3_bind(c, smem_raw, L);
@@ -981,7 +1006,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
             const int tl = s_tlevel[k & 1], nt0 = s_nt;
             while (true) {
                 int n = 0, reason = kWalkEnd;
-                if (lane == 0) reason = v3_walk_serial(c, r, k, tl, &n);
+                if (lane == 0) reason = v3_walk_serial(c, r, k, tl, &n, &s_io);
                 reason = __shfl_sync(0xffffffffu, reason, 0);
                 n = __shfl_sync(0xffffffffu, n, 0);
                 if (n > 0) {                                             // bookkeeping of the queued tokens, one lane each
