@@ -406,6 +406,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         c->stats.slow_main = c->h_v3c.slow; c->stats.window_hits = c->h_v3c.linkwalk; c->stats.windows = c->h_v3c.windows;
         c->stats.cyc_spec = c->h_v3c.cyc_spec; c->stats.cyc_resolve = c->h_v3c.cyc_resolve; c->stats.general_path = c->h_v3c.general;
         c->stats.cyc_total = c->h_v3c.cyc_total; c->stats.flagged = c->h_v3c.flagged;
+        if (getenv("ZLB_V3_TRACE")) fprintf(stderr, "v3: tokens %llu resolve %llu special %llu cycles, flagged %llu general %llu slow %llu\n", c->h_v3c.tokens, c->h_v3c.cyc_resolve, c->h_v3c.cyc_special, c->h_v3c.flagged, c->h_v3c.general, c->h_v3c.slow);
     } else if (c->parse_version == 2) {
         CU(cudaMemcpyAsync(&c->h_v2c, c->d_v2c, sizeof(V2Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

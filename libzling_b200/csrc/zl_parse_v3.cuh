@@ -109,7 +109,7 @@ ZL_HD uint32_t z3_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout -------------------------------------------------------------------------------------------
 struct V3Layout {
     int dmax, lmax;
-    int rb, key, link, blink, ins, suf, tw, last, cnt, snap, mru, pcnt, bq, tab[2], total;
+    int rb, key, link, blink, ins, suf, tw, last, cnt, snap, mru, pcnt, tab[2], total;
     int t_hdr, t_node, t_eq, t_dec, t_size;          // offsets inside one table
 };
 __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
@@ -128,7 +128,6 @@ __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
     L.snap  = take(4 * 256 * 3);
     L.mru   = take(4 * 256);
     L.pcnt  = take(4 * 256 * 2);
-    L.bq    = take(4 * 32);
     const int n = kV3W + 2;
     int t = 0;
     auto ttake = [&](int bytes) { int o = t; t += (bytes + 15) & ~15; return o; };
@@ -149,7 +148,7 @@ struct V3Ctx {
     // shared memory
     uint32_t* rbw;                              // input bytes, ring of kV3R bytes viewed as words
     uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* ins; uint16_t* suf; uint32_t* tw;
-    uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru; uint32_t* pcnt; uint32_t* bq;
+    uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru; uint32_t* pcnt;
     uint8_t* tab0; int tab_stride, t_hdr, t_node, t_eq, t_dec;   // two tables, selected arithmetically (no dynamic struct indexing)
     int dmax, lmax;
 };
@@ -164,7 +163,7 @@ __host__ __device__ inline void v3_bind(V3Ctx& c, uint8_t* smem, const V3Layout&
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
     c.blink = (uint16_t*) (smem + L.blink); c.ins = (uint32_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf); c.tw = (uint32_t*) (smem + L.tw);
     c.last = (uint32_t*) (smem + L.last); c.cnt = (uint32_t*) (smem + L.cnt); c.snap = (uint32_t*) (smem + L.snap);
-    c.mru = (uint32_t*) (smem + L.mru); c.pcnt = (uint32_t*) (smem + L.pcnt); c.bq = (uint32_t*) (smem + L.bq);
+    c.mru = (uint32_t*) (smem + L.mru); c.pcnt = (uint32_t*) (smem + L.pcnt);
     c.tab0 = smem + L.tab[0]; c.tab_stride = L.tab[1] - L.tab[0];
     c.t_hdr = L.t_hdr; c.t_node = L.t_node; c.t_eq = L.t_eq; c.t_dec = L.t_dec;
     c.dmax = L.dmax; c.lmax = L.lmax;
@@ -451,6 +450,7 @@ struct V3Run {                       // resolver state carried across windows (o
     int skip_push;                   // no push is pending on arrival (block start: the two raw bytes push nothing)
     int tail;                        // ip reached the last 275 bytes: the rest is done by v3_resolve_tail
     uint32_t n_general, n_slow, n_linkwalk, n_flagged;
+    long long cyc_special;          // device: cycles spent on flagged tokens (hazard check + general path)
 };
 
 // GetCommonLength with both operands inside the byte ring
@@ -737,150 +737,90 @@ ZL_HD void v3_rollover(const V3Ctx& c, V3Run& r, int nt) {                // sub
     r.op = 0; r.tok_begin = nt; r.enc_begin = r.ip;
 }
 
-// ---- the walker -----------------------------------------------------------------------------------------------------
-// Tokens starting in window k (EncodeImpl, lz.cpp:139-195), probe region only (x + 275 < ilen), in three pieces:
-//   v3_walk_serial    one thread.  The irreducibly serial part of a token whose frozen decision is unflagged: one
-//                     16-byte decision load, the word-MRU push of the token that ended here, the word test when no
-//                     match is taken, advance.  The token is queued (position | kind), nothing else is touched.
-//   v3_batch_flush    the queued tokens' bookkeeping — per-context insert counters (ring heads) and the per-position
-//                     marks — done for up to 32 tokens at once by the resolver warp (host replay: in order).
-//   v3_token_special  one thread, after a flush: a token with a hazard flag, a level mismatch or a full sub-block:
-//                     hazard check, general path, sub-block roll-over; books itself.
-// Token words, literal lists and bucket writes are produced from the marks by all threads after the window
-// (v3_token_of / v3_apply_position).
-constexpr int kV3Batch = 32;
-enum { kWalkEnd = 0, kWalkFull = 1, kWalkSpecial = 2 };
-
-// The hot loop lives in its own non-inlined function so that its instructions are contiguous (the resolver is one
-// thread: it has nobody to hide instruction-fetch latency behind, and the kernel around it is > 150 KB of code).
-// Shared memory is addressed explicitly on the device (32-bit shared-window addresses), by pointer on the host.
-#if defined(__CUDA_ARCH__)
-typedef uint32_t z3_sptr;
-__device__ __forceinline__ z3_sptr z3_sp(const void* p) { return (z3_sptr) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint4 z3_lds128(z3_sptr a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t z3_lds32(z3_sptr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void z3_sts32(z3_sptr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-#else
-typedef uintptr_t z3_sptr;
-inline z3_sptr z3_sp(const void* p) { return (z3_sptr) p; }
-inline uint4 z3_lds128(z3_sptr a) { return *reinterpret_cast<const uint4*>(a); }
-inline uint32_t z3_lds32(z3_sptr a) { return *reinterpret_cast<const uint32_t*>(a); }
-inline void z3_sts32(z3_sptr a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
-#endif
-struct V3WalkIO { int x, op, n, reason; uint32_t prev_lit, skip_push; };
-
-// dec0 = address of dec[0] (position 0, i.e. table base - k W entries), 16 bytes per position
-__host__ __device__ __noinline__ void v3_walk_core(z3_sptr dec0, z3_sptr mru, z3_sptr bq, int wend, int xmax, uint32_t force, V3WalkIO* io) {
-    int x = io->x, op = io->op, n = 0, reason = kWalkEnd;
-    uint32_t prev_lit = io->prev_lit, skip_push = io->skip_push;
-    uint4 d = z3_lds128(dec0 + (z3_sptr) x * 16u);
-    while (true) {
-        const uint32_t c3 = d.z & 0xffu, pw = d.z >> 8, ctx = d.y >> 24;
-        const uint32_t m = z3_lds32(mru + c3 * 4u);
-        const uint32_t flen = d.x & 511u;
-        // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
-        if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) z3_sts32(mru + c3 * 4u, pw | (m << 16));
-        skip_push = 0;
-        if ((((d.y & kF_ANY) | force) != 0) | (op + 1 >= kSubSymbols)) {
-            skip_push = 1;                                               // the push for x is done; the special handler must not repeat it
-            reason = kWalkSpecial;
-            break;
-        }
-        if (flen) {                                                      // clean match
-            z3_sts32(bq + (z3_sptr) n * 4u, (uint32_t) x | (kKindMatch << 24));
-            n++; op += 2; prev_lit = 0; x += (int) flen;
-            if (x >= wend) break;
-            d = z3_lds128(dec0 + (z3_sptr) (x < xmax ? x : xmax) * 16u);
-        } else {                                                         // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
-            const uint4 dA = z3_lds128(dec0 + (z3_sptr) (x + 1) * 16u), dB = z3_lds128(dec0 + (z3_sptr) (x + 2) * 16u);
-            const uint32_t m1 = z3_lds32(mru + ctx * 4u);
-            const bool w0 = (m1 & 0xffffu) == d.w, w1 = (m1 >> 16) == d.w;
-            const uint32_t kind = w0 ? kKindWord0 : (w1 ? kKindWord1 : kKindLit);
-            z3_sts32(bq + (z3_sptr) n * 4u, (uint32_t) x | (kind << 24));
-            n++; op += 1; prev_lit = kind == kKindLit;
-            x += (w0 || w1) ? 2 : 1;                                     // a word-257 hit's MRU update is the push made on arrival at x + 2
-            d = (w0 || w1) ? dB : dA;
-            if (x >= wend) break;
-        }
-        if (n == kV3Batch) { reason = kWalkFull; break; }
-    }
-    io->x = x; io->op = op; io->n = n; io->reason = reason; io->prev_lit = prev_lit; io->skip_push = skip_push;
-}
-
-ZL_HD int v3_walk_serial(const V3Ctx& c, V3Run& r, int k, int tlevel, int* n_out, V3WalkIO* io) {
-    *n_out = 0;
-    if (r.tail) return kWalkEnd;
+// Tokens starting in window k (EncodeImpl, lz.cpp:139-195), probe region only (x + 275 < ilen).  The walker does
+// the minimum that is serial: one 16-byte decision load, the word-MRU push of the token that ended here, the
+// context's insert counter, and a per-position mark; token words, literal lists and bucket writes are produced
+// from the marks by all threads afterwards (v3_token_of / v3_apply_position).  nt0 = tokens emitted before window k.
+// The common path is straight-line code (selects, no branches) so that its independent strands overlap; the
+// decisions of both possible next positions are loaded speculatively.
+ZL_HD void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
+    if (r.tail) return;
+    V3Win w = v3_window(c, k, r.level, tlevel);
+    const uint4* dec = w.t.dec - k * kV3W;                               // dec[x] for x in the table
     const int lim = c.ilen - kGuard;                                     // probes happen at x < lim (lz.cpp:158)
     const int wend = (k + 1) * kV3W < lim ? (k + 1) * kV3W : lim;
     const int xmax = (k + 1) * kV3W + 1;                                 // last position the table holds
-    if (r.ip >= wend) { if (r.ip >= lim) r.tail = 1; return kWalkEnd; }
-    io->x = r.ip; io->op = r.op; io->prev_lit = (uint32_t) r.prev_lit; io->skip_push = (uint32_t) r.skip_push;
-    v3_walk_core(z3_sp(v3_table(c, k).dec) - (z3_sptr) (k * kV3W) * 16u, z3_sp(c.mru), z3_sp(c.bq), wend, xmax, r.level != tlevel ? kF_FORCE : 0u, io);
-    r.ip = io->x; r.op = io->op; r.prev_lit = (int) io->prev_lit; r.skip_push = (int) io->skip_push;
-    if (io->reason != kWalkSpecial && r.ip >= lim) r.tail = 1;
-    *n_out = io->n;
-    return io->reason;
-}
-
-// bookkeeping of one queued token (host replay and reference form of the warp-wide flush in the kernel)
-ZL_HD void v3_batch_apply_one(const V3Ctx& c, uint32_t e) {
-    const int x = (int) (e & 0xffffffu);
-    const uint32_t ctx = v3_rb8(c.rbw, (uint32_t) x - 1);
-    const uint32_t cn = c.cnt[ctx] + 1u;
-    c.cnt[ctx] = cn;
-    c.ins[x & (kV3R - 1)] = (cn & (kRing - 1)) | ((e >> 24) << 12);
-}
-
-// the token at r.ip whose decision is flagged / whose sub-block is full; its word-MRU push has been made already
-ZL_HD void v3_token_special(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {   // (inlined: it needs the whole context)
-    const int x = r.ip;
-    const uint4 d = v3_table(c, k).dec[x - k * kV3W];
-    const int lim = c.ilen - kGuard;
-    if (r.op + 1 >= kSubSymbols) v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));    // rare: the sub-block is full
-    const V3Win w = v3_window(c, k, r.level, tlevel);
-    const uint32_t ctx = d.y >> 24;
-    const uint32_t cn = c.cnt[ctx] + 1u;
-    uint32_t flen = d.x & 511u;
-    uint32_t mark = cn & (kRing - 1);
-    const bool force = r.level != tlevel;
-    if (((d.y & kF_ANY) != 0) || force) {                                // flagged: most flags turn out not to hold
-        r.n_flagged++;
-#if defined(ZL_V3_FLAG_HIST) && !defined(__CUDA_ARCH__)
-        g_flag_hist[((d.y >> 16) & 0x7fu) | (force ? 0x80u : 0u)]++;
+    int x = r.ip, op = r.op;
+    uint32_t prev_lit = (uint32_t) r.prev_lit, skip_push = (uint32_t) r.skip_push;
+    uint32_t force = r.level != tlevel ? kF_FORCE : 0u;
+    if (x >= wend) { if (x >= lim) r.tail = 1; return; }
+    uint4 d = dec[x];
+    while (true) {
+        uint32_t flen = d.x & 511u;
+        // the decisions of both possible next positions are requested first: shared-memory loads are not moved across
+        // the stores below by the compiler, and the chain x -> decision -> next x is the critical path
+        const int xa0 = x + (flen ? (int) flen : 1);
+        const uint4 dA0 = dec[xa0 < xmax ? xa0 : xmax], dB = dec[x + 2];
+        const uint32_t c3 = d.z & 0xffu, pw = d.z >> 8, ctx = d.y >> 24;
+        const uint32_t m = c.mru[c3];
+        const uint32_t cn = c.cnt[ctx] + 1u;
+        // word-MRU push of the token that ended at x: unconditional after a literal, else only if the top differs
+        if (!skip_push && (prev_lit || (m & 0xffffu) != pw)) c.mru[c3] = pw | (m << 16);
+        skip_push = 0;
+        const bool special = ((d.y & kF_ANY) | force) != 0 || op + 1 >= kSubSymbols;
+        if (!special && flen) {                                          // clean match (55 % of the tokens): the short way round
+            c.cnt[ctx] = cn;
+            c.ins[x & (kV3R - 1)] = (cn & (kRing - 1)) | (kKindMatch << 12);
+            op += 2; prev_lit = 0; x = xa0; d = dA0;
+            if (x >= wend) break;
+            continue;
+        }
+        if (__builtin_expect(op + 1 >= kSubSymbols, 0)) {                // rare: the sub-block is full
+            r.ip = x; r.op = op;
+            v3_rollover(c, r, nt0 + v3_count_marks(c, k * kV3W, x));
+            op = 0;
+            force = r.level != tlevel ? kF_FORCE : 0u;
+            w = v3_window(c, k, r.level, tlevel);
+        }
+        uint32_t mark = cn & (kRing - 1);
+        if (__builtin_expect(((d.y & kF_ANY) | force) != 0, 0)) {        // flagged: most flags turn out not to hold
+            r.n_flagged++;
+#if defined(__CUDA_ARCH__)
+            const long long t_sp = clock64();
 #endif
-        if (force || v3_hazard(c, w, x, d, cn)) {
-            uint32_t midx = 0;
-            flen = (uint32_t) v3_probe_general(c, r, w, x, d, &midx);
-            mark |= kInsExplicit;
-            if (flen) c.tw[x & (kV3R - 1)] = tok_match(flen, midx);
+#if defined(ZL_V3_FLAG_HIST) && !defined(__CUDA_ARCH__)
+            g_flag_hist[((d.y >> 16) & 0x7fu) | (force ? 0x80u : 0u)]++;
+#endif
+            if (force || v3_hazard(c, w, x, d, cn)) {
+                uint32_t midx = 0;
+                flen = (uint32_t) v3_probe_general(c, r, w, x, d, &midx);
+                mark |= kInsExplicit;
+                if (flen) c.tw[x & (kV3R - 1)] = tok_match(flen, midx);
+            } else {
+                c.cnt[ctx] = cn;
+            }
+#if defined(__CUDA_ARCH__)
+            r.cyc_special += clock64() - t_sp;
+#endif
         } else {
             c.cnt[ctx] = cn;
         }
-    } else {
-        c.cnt[ctx] = cn;
+        // next position: x + flen after a match, else x + 2 after a word hit, x + 1 after a literal
+ const int xa = x + (flen ? (int) flen : 1), xb = x + 2;
+        const uint4 dA = xa == xa0 ? dA0 : dec[xa < xmax ? xa : xmax];   // the general path may have changed the length
+        const uint32_t m1 = c.mru[ctx];                                  // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
+        const bool w0 = (m1 & 0xffffu) == d.w, w1 = (m1 >> 16) == d.w;
+        const bool word = !flen && (w0 || w1);
+        const uint32_t kind = flen ? kKindMatch : (w0 ? kKindWord0 : (w1 ? kKindWord1 : kKindLit));
+        c.ins[x & (kV3R - 1)] = mark | (kind << 12);
+        prev_lit = kind == kKindLit;
+        op += flen ? 2 : 1;
+        x = word ? xb : xa;
+        d = word ? dB : dA;
+        if (x >= wend) break;
     }
-    const uint32_t m1 = c.mru[ctx];
-    const bool w0 = (m1 & 0xffffu) == d.w, w1 = (m1 >> 16) == d.w;
-    const bool word = !flen && (w0 || w1);
-    const uint32_t kind = flen ? kKindMatch : (w0 ? kKindWord0 : (w1 ? kKindWord1 : kKindLit));
-    c.ins[x & (kV3R - 1)] = mark | (kind << 12);
-    r.prev_lit = kind == kKindLit;
-    r.op += flen ? 2 : 1;
-    r.ip = x + (flen ? (int) flen : (word ? 2 : 1));
-    r.skip_push = 0;                                                     // the next token's arrival push is due again
-    if (r.ip >= lim) r.tail = 1;
-}
-
-// host form of RESOLVE(k) (the kernel runs the same three pieces with the flush spread over the resolver warp)
-inline void v3_resolve_window(const V3Ctx& c, V3Run& r, int k, int tlevel, int nt0) {
-    V3WalkIO io;
-    while (true) {
-        int n = 0;
-        const int reason = v3_walk_serial(c, r, k, tlevel, &n, &io);
-        for (int t = 0; t < n; t++) v3_batch_apply_one(c, c.bq[t]);
-        if (reason == kWalkSpecial) v3_token_special(c, r, k, tlevel, nt0);
-        else if (reason == kWalkEnd) break;
-    }
+    r.ip = x; r.op = op; r.prev_lit = (int) prev_lit; r.skip_push = (int) skip_push;
+    if (x >= lim) r.tail = 1;
 }
 
 // The last 275 bytes of the block (no probe, no insert: lz.cpp:158) and blocks shorter than that: plain serial
@@ -914,7 +854,7 @@ ZL_HD void v3_resolve_tail(const V3Ctx& c, V3Run& r, int* nt_io, int* nl_io) {
 }
 
 #if defined(__CUDACC__)
-struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows, cyc_resolve, cyc_spec, cyc_total, flagged; };
+struct V3Counters { unsigned long long tokens, general, slow, linkwalk, windows, cyc_resolve, cyc_spec, cyc_total, flagged, cyc_special; };
 
 __device__ __forceinline__ void v3_bar_producers() { asm volatile("bar.sync 1, %0;" :: "n"(kV3Prod) : "memory"); }
 
@@ -924,7 +864,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int s_level, s_tlevel[2], s_nt, s_nl, s_wtok[kV3Threads / 32], s_wlit[kV3Threads / 32];
-    __shared__ V3WalkIO s_io;
     const V3Layout L = v3_layout(dmax, lmax);
     V3Ctx c;
     v3_bind(c, smem_raw, L);
@@ -943,7 +882,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     V3Run r;
     r.ip = 0; r.op = 0; r.j = 0; r.level = 0; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
     r.enc_begin = 0; r.level = v3_next_level(c, r, 0);
-    r.n_general = 0; r.n_slow = 0; r.n_linkwalk = 0; r.n_flagged = 0;
+    r.n_general = 0; r.n_slow = 0; r.n_linkwalk = 0; r.n_flagged = 0; r.cyc_special = 0;
     long long cyc_res = 0, cyc_spec = 0;
     const long long t_begin = clock64();
     if (tid == 0) {
@@ -1001,34 +940,10 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
             }
         }
         if (serialize) __syncthreads();                                  // experiment: RESOLVE(k) after SPEC(k+1) instead of beside it
-        if (warp == 0 && k >= 0) {                                       // RESOLVE(k): lane 0 walks, the warp flushes
+        if (tid == 0 && k >= 0) {
             const long long t0 = clock64();
-            const int tl = s_tlevel[k & 1], nt0 = s_nt;
-            while (true) {
-                int n = 0, reason = kWalkEnd;
-                if (lane == 0) reason = v3_walk_serial(c, r, k, tl, &n, &s_io);
-                reason = __shfl_sync(0xffffffffu, reason, 0);
-                n = __shfl_sync(0xffffffffu, n, 0);
-                if (n > 0) {                                             // bookkeeping of the queued tokens, one lane each
-                    const bool live = lane < n;
-                    const uint32_t e = live ? c.bq[lane] : 0u;
-                    const int x = (int) (e & 0xffffffu);
-                    const uint32_t ctx = live ? v3_rb8(c.rbw, (uint32_t) x - 1) : 256u + (uint32_t) lane;
-                    const uint32_t grp = __match_any_sync(0xffffffffu, ctx);
-                    const uint32_t rank = (uint32_t) __popc(grp & ((2u << lane) - 1u));          // 1-based among the group's lanes <= lane
-                    uint32_t cn = 0;
-                    if (live) cn = c.cnt[ctx] + rank;
-                    __syncwarp();                                        // every lane has read its counter before any is advanced
-                    if (live) {
-                        c.ins[x & (kV3R - 1)] = (cn & (kRing - 1)) | ((e >> 24) << 12);
-                        if ((grp >> lane) == 1u) c.cnt[ctx] = cn;        // the group's last lane holds the new counter
-                    }
-                }
-                __syncwarp();
-                if (reason == kWalkSpecial) { if (lane == 0) v3_token_special(c, r, k, tl, nt0); __syncwarp(); }
-                else if (reason == kWalkEnd) break;
-            }
-            if (lane == 0) cyc_res += clock64() - t0;
+            v3_resolve_window(c, r, k, s_tlevel[k & 1], s_nt);
+            cyc_res += clock64() - t0;
         }
         __syncthreads();
         if (k >= 0) {                                                    // APPLY(k) + EMIT(k) + counter snapshot k+1
@@ -1073,6 +988,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
             atomicAdd(&counters->windows, (unsigned long long) nwin);
             atomicAdd(&counters->cyc_resolve, (unsigned long long) cyc_res);
             atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));
+            atomicAdd(&counters->cyc_special, (unsigned long long) r.cyc_special);
         }
     }
     if (tid == 33 && counters) atomicAdd(&counters->cyc_spec, (unsigned long long) cyc_spec);

@@ -20,6 +20,5 @@ fi
 if [ "$2" == "full" ]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/${TAG}_ncu_bench.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:zl_rolz_parse_v3 -c 1 -o gpurun_out/${TAG}_parse_v3 -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full.log 2>&1
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:zl_mtf_ctx -c 1 -o gpurun_out/${TAG}_mtf_ctx -f python bench.py --steps 1 --warmup 0 --skip-parity > gpurun_out/${TAG}_ncu_full2.log 2>&1
-  ls -la gpurun_out | tail -12
+  ls -la gpurun_out | tail -8
 fi
