@@ -399,17 +399,17 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
                                                         const uint8_t* state_in, uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
     const int ctx = blockIdx.x, lane = threadIdx.x;
     __shared__ __align__(16) uint8_t s_sym[256];          // rank -> byte
-    __shared__ __align__(16) uint16_t s_r2[256];          // byte -> rank | mtf_next(rank) << 8: ONE load gives both swap positions
+    __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
     __shared__ __align__(16) uint8_t s_out[kMtfChunk];
     __shared__ __align__(16) uint8_t s_byte[2][kMtfChunk + 16];
-    __shared__ __align__(16) uint8_t s_next[256];         // mtf_next() as a table
+    __shared__ __align__(16) uint8_t s_next[256];         // mtf_next() as a table: one load instead of a multiply-divide chain
     for (int i = lane; i < 256; i += 32) s_next[i] = (uint8_t) mtf_next(i);
     {
         const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
         for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
         __syncwarp();
-        for (int i = lane; i < 256; i += 32) s_r2[s_sym[i]] = (uint16_t) (i | (mtf_next(i) << 8));
+        for (int i = lane; i < 256; i += 32) s_rank[s_sym[i]] = (uint8_t) i;
         __syncwarp();
     }
     for (int b = first_block; b < nblocks; b++) {
@@ -432,24 +432,24 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
             __syncwarp();
             const int cnt = min(kMtfChunk, n - base);
             if (lane == 0) {
-                // Two literals per step (ZlingMTFEncoder::Encode, lz.cpp:112-117, twice): the second one's table reads
-                // are issued together with the first one's and patched from registers where the first literal's swap
-                // touches them (a swap moves two entries).  Bytes come four at a time (prefetched one step ahead), ranks
-                // leave four at a time; the token words are written by all lanes after the chunk.
+                // Two literals per step: the second one's table reads are issued together with the first one's and
+                // patched from registers where the first literal's swap touches them (the swap moves two entries).
+                // Bytes come four at a time (prefetched one step ahead), ranks leave four at a time; the token
+                // words are written by all lanes after the chunk.
                 #define ZL_MTF_PAIR(bA, bB, rA, rB) {                                                              \
-                    const uint32_t vA = s_r2[bA], vB = s_r2[bB];                                                  \
-                    const uint32_t iA = vA & 0xffu, jA = vA >> 8;                                                 \
-                    uint32_t iB = vB & 0xffu, jB = vB >> 8;                                                       \
-                    const uint32_t oA = s_sym[jA], njA = s_next[jA];                                              \
-                    uint32_t oBr = s_sym[jB], njB = s_next[jB];                                                   \
-                    if (bB == bA) { iB = jA; jB = njA; oBr = s_sym[jB]; njB = s_next[jB]; }                       \
-                    else if (bB == oA) { iB = iA; jB = jA; njB = njA; }                                           \
+                    const int iA = s_rank[bA], iBr = s_rank[bB];                                                  \
+                    const int jA = s_next[iA];                                                                    \
+                    int iB = bB == bA ? jA : iBr;                       /* assumes bB is not the byte A swaps with */ \
+                    int jB = s_next[iB];                                                                          \
+                    const uint32_t oA = s_sym[jA];                                                                \
+                    uint32_t oBr = s_sym[jB];                                                                     \
+                    if (bB == oA && bB != bA) { iB = iA; jB = s_next[iB]; oBr = s_sym[jB]; }                      \
                     const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);                                    \
                     s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;                                           \
-                    s_r2[oA] = (uint16_t) (iA | (jA << 8)); s_r2[bA] = (uint16_t) (jA | (njA << 8));              \
+                    s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;                                         \
                     s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;                                           \
-                    s_r2[oB] = (uint16_t) (iB | (jB << 8)); s_r2[bB] = (uint16_t) (jB | (njB << 8));              \
-                    rA = iA; rB = iB; }
+                    s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;                                         \
+                    rA = (uint32_t) iA; rB = (uint32_t) iB; }
                 int q = 0;
                 const uint32_t* byte4 = reinterpret_cast<const uint32_t*>(s_byte[buf]);
                 uint32_t* out4 = reinterpret_cast<uint32_t*>(s_out);
@@ -466,10 +466,10 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
                 #undef ZL_MTF_PAIR
                 for (; q < cnt; q++) {
                     const uint32_t byte = s_byte[buf][q];
-                    const uint32_t v = s_r2[byte], i = v & 0xffu, jn = v >> 8;
-                    const uint32_t other = s_sym[jn], njn = s_next[jn];
+                    const int i = s_rank[byte], jn = s_next[i];
+                    const uint32_t other = s_sym[jn];
                     s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;
-                    s_r2[other] = (uint16_t) (i | (jn << 8)); s_r2[byte] = (uint16_t) (jn | (njn << 8));
+                    s_rank[other] = (uint8_t) i; s_rank[byte] = (uint8_t) jn;
                     s_out[q] = (uint8_t) i;
                 }
             }
