@@ -51,9 +51,8 @@ def load_traffic(nbytes, level):
         with open(p) as f:
             t = json.load(f)
         if int(t.get("workload_bytes", -1)) == int(nbytes) and int(t.get("level", -1)) == int(level):
-            return {"GB_per_launch": round((t["dram_bytes_read"] + t["dram_bytes_write"]) / 1e9, 4), "algorithmic_GB_per_launch": round(nbytes / 1e9, 4),
-                    "source": t.get("source")}
-    return None
+            return int(t["dram_bytes_read"] + t["dram_bytes_write"]), t.get("source")
+    return None, None
 
 
 class ClockSampler:
@@ -158,6 +157,7 @@ def main():
     ap.add_argument("--size-mb", type=float, default=100.0)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--no-decode", action="store_true", help="skip the secondary decode leg")
     ap.add_argument("--corpus", default="enwik8", choices=["enwik8", "mixed"], help="mixed = BASELINE.json configs[3] (text + binary + random)")
     args = ap.parse_args()
 
@@ -275,7 +275,7 @@ def main():
     # ---- secondary: decode (BASELINE.json configs[4] shape) on a bounded sample — the first 16 MiB block of the stream.
     # One chain per stream (MTF state + context dependence): reported, not optimised for, next to the CPU decoder.
     decode = None
-    if rank == 0:
+    if rank == 0 and not args.no_decode:
         from _libs import Ref, Oracle, have_ref, bound  # noqa: F401
         sample = data[: min(nbytes, libzling_b200.BLOCK)]
         zs = ctx.encode(sample, args.level)
@@ -304,6 +304,7 @@ def main():
     value = world * nbytes / 1e6 / (ms_step / 1e3)
     e2e_value = world * nbytes / 1e6 / e2e_step
     peak, peak_src = load_peaks()
+    traffic, traffic_src = load_traffic(nbytes, args.level)
     pms = float(np.mean(parse_ms))
     ach = nbytes / 1e9 / (pms / 1e3) if pms > 0 else 0.0      # algorithmic bytes of the parse launch: every input byte read once
     if rank == 0:
@@ -322,7 +323,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "zl_rolz_parse_v%s (one launch per step, 1 CTA per 16 MiB block)" % os.environ.get("ZLB_PARSE", "3"),
-                         "achieved": round(ach, 4), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": load_traffic(nbytes, args.level),
+                         "achieved": round(ach, 4), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                         "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(nbytes),
                          "peak_source": peak_src,
                          "note": "algorithmic bytes = input bytes (each read once); the kernel is bound by the serial token chain, not HBM "
                                  "(DESIGN.md §4): %d tokens in %d chains" % (last["tokens"], nblocks)},

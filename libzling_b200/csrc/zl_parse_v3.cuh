@@ -27,7 +27,10 @@
 
 namespace zl {
 
-constexpr int kV3Prod    = 384;                 // producer threads: the 12 warps of SM sub-partitions 1..3
+#ifndef ZL_V3_PROD
+#define ZL_V3_PROD 384
+#endif
+constexpr int kV3Prod    = ZL_V3_PROD;          // producer threads: up to the 12 warps of SM sub-partitions 1..3 (a multiple of 32)
 constexpr int kV3Threads = 512;                 // 16 warps (128 registers per thread); warp 0 = resolver, alone on sub-partition 0:
                                                 // warps 4, 8, 12 only help in the short APPLY/EMIT phases, so the resolver keeps its
                                                 // scheduler and instruction cache to itself
@@ -109,7 +112,7 @@ ZL_HD uint32_t z3_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout -------------------------------------------------------------------------------------------
 struct V3Layout {
     int dmax, lmax;
-    int rb, key, link, blink, ins, suf, tw, last, cnt, snap, mru, pcnt, tab[2], total;
+    int rb, key, link, blink, llen, ins, suf, tw, last, cnt, snap, mru, pcnt, tab[2], total;
     int t_hdr, t_node, t_eq, t_dec, t_size;          // offsets inside one table
 };
 __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
@@ -120,6 +123,7 @@ __host__ __device__ inline V3Layout v3_layout(int dmax, int lmax) {
     L.key   = take(4 * kV3R);
     L.link  = take(2 * kV3R);
     L.blink = take(2 * kV3R);
+    L.llen  = take(2 * kV3R);
     L.ins   = take(4 * kV3R);
     L.suf   = take(2 * kV3R);
     L.tw    = take(4 * kV3R);
@@ -147,7 +151,7 @@ struct V3Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory
     uint32_t* rbw;                              // input bytes, ring of kV3R bytes viewed as words
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* ins; uint16_t* suf; uint32_t* tw;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* llen; uint32_t* ins; uint16_t* suf; uint32_t* tw;
     uint32_t* last; uint32_t* cnt; uint32_t* snap; uint32_t* mru; uint32_t* pcnt;
     uint8_t* tab0; int tab_stride, t_hdr, t_node, t_eq, t_dec;   // two tables, selected arithmetically (no dynamic struct indexing)
     int dmax, lmax;
@@ -161,7 +165,7 @@ ZL_HD V3Table v3_table(const V3Ctx& c, int j) {
 
 __host__ __device__ inline void v3_bind(V3Ctx& c, uint8_t* smem, const V3Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.ins = (uint32_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf); c.tw = (uint32_t*) (smem + L.tw);
+    c.blink = (uint16_t*) (smem + L.blink); c.llen = (uint16_t*) (smem + L.llen); c.ins = (uint32_t*) (smem + L.ins); c.suf = (uint16_t*) (smem + L.suf); c.tw = (uint32_t*) (smem + L.tw);
     c.last = (uint32_t*) (smem + L.last); c.cnt = (uint32_t*) (smem + L.cnt); c.snap = (uint32_t*) (smem + L.snap);
     c.mru = (uint32_t*) (smem + L.mru); c.pcnt = (uint32_t*) (smem + L.pcnt);
     c.tab0 = smem + L.tab[0]; c.tab_stride = L.tab[1] - L.tab[0];
@@ -236,7 +240,9 @@ inline void v3_bucket_pass_serial(const V3Ctx& c, int lo, int hi) {
     }
 }
 
-// ---- SPEC phase C: nearest earlier position with the same key, not before `lb` -------------------------------------
+ZL_HD int v3_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q);
+
+// ---- SPEC phase C: nearest earlier position with the same key, not before `lb`, and the match length against it ------
 ZL_HD void v3_link_position(const V3Ctx& c, int x, int lb) {
     const uint32_t k = c.key[x & (kV3R - 1)];
     uint32_t out = 0;
@@ -251,6 +257,8 @@ ZL_HD void v3_link_position(const V3Ctx& c, int x, int lb) {
         }
     }
     c.link[x & (kV3R - 1)] = (uint16_t) out;
+    // GetCommonLength against that position: the candidate the resolver's general path needs most often
+    c.llen[x & (kV3R - 1)] = out ? (uint16_t) v3_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) x - out) : (uint16_t) 0;
 }
 
 // ---- SPEC phase D: chain record of a position against the frozen bucket state ---------------------------------------
@@ -627,7 +635,8 @@ ZL_HD int v3_probe_general(const V3Ctx& c, V3Run& r, const V3Win& w, int x, cons
             if (visited < D && !done) {
                 visited++;
                 if ((c.key[y & (kV3R - 1)] >> 21) == chk) {
-                    const int l = v3_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) y);
+                    const int l = y == x - (int) c.link[x & (kV3R - 1)] ? (int) c.llen[x & (kV3R - 1)]      // precomputed by SPEC
+                                                                        : v3_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) y);
                     if (l > best) { best = l; bestslot = m & (kRing - 1); if (best == kMaxLen) done = true; }
                 }
             } else break;
@@ -872,8 +881,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) zl_rolz_parse_v3_kernel(ParseAr
     c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
     c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock; c.base_level = base_level;
     const int ilen = c.ilen;
-    const bool producer = (warp & 3) != 0;                               // a warp runs on sub-partition warp % 4
-    const int ptid = (warp - 1 - (warp >> 2)) * 32 + lane;               // 0 .. kV3Prod-1 over the producer warps
+    const int pwarp = warp - 1 - (warp >> 2);                            // producer warp index over the warps with warp % 4 != 0
+    const bool producer = (warp & 3) != 0 && pwarp < kV3Prod / 32;       // a warp runs on sub-partition warp % 4
+    const int ptid = pwarp * 32 + lane;                                  // 0 .. kV3Prod-1 over the producer warps
 
     for (int i = tid; i < 256; i += kV3Threads) { c.cnt[i] = 0; c.mru[i] = 0; c.snap[i] = 0; c.snap[256 + i] = 0; c.snap[512 + i] = 0; c.pcnt[i] = 0; c.pcnt[256 + i] = 0; }
     for (int i = tid; i < kV3Buckets; i += kV3Threads) c.last[i] = 0;
