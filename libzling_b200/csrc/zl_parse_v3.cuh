@@ -4,7 +4,7 @@
 // chain per block.  v2 (zl_parse_v2.cuh) alternated "speculate a window" / "resolve a window"; its resolver spent
 // ~1300 cycles per token on warp-wide hazard scans.  v3 keeps v2's exactness argument and changes the schedule:
 //
-//   producers (12 warps)   SPEC(k+1): for every position of window k+1 walk its hash chain in the bucket state G
+//   producers (8 warps)    SPEC(k+1): for every position of window k+1 walk its hash chain in the bucket state G
 //                          frozen at the START OF WINDOW k (G is only written between steps, see APPLY), record
 //                          up to dmax nodes with match lengths, byte-equality maps for the lazy probes, the link
 //                          to the nearest earlier position with the same (context, hash slot) key, and the
@@ -28,7 +28,7 @@
 namespace zl {
 
 #ifndef ZL_V3_PROD
-#define ZL_V3_PROD 384
+#define ZL_V3_PROD 256
 #endif
 constexpr int kV3Prod    = ZL_V3_PROD;          // producer threads: up to the 12 warps of SM sub-partitions 1..3 (a multiple of 32)
 constexpr int kV3Threads = 512;                 // 16 warps (128 registers per thread); warp 0 = resolver, alone on sub-partition 0:
