@@ -63,6 +63,7 @@ struct zlb_ctx {
     zlb_stats stats = {};
     int last_nblocks = 0;
     int parse_version = 3;          // ZLB_PARSE=1: literal one-warp-per-block chain walker, 2: windowed speculate/resolve, 3: pipelined (default)
+    const void* pending = nullptr;  // encoder with a submitted, not yet completed range: it owns the context's buffers
     int v3_serialize = 0;           // ZLB_V3_SERIAL=1: experiment, run RESOLVE(k) after SPEC(k+1) instead of concurrently
     int mtf_version = 2;            // ZLB_MTF=1: one warp per stream, 2: one CTA per context (default)
     V2Counters* d_v2c = nullptr;
@@ -219,6 +220,7 @@ zlb_encoder* zlb_encoder_begin(zlb_ctx* c, int level) {
 void zlb_encoder_end(zlb_encoder* e) {
     if (!e) return;
     cudaSetDevice(e->ctx->device);
+    if (e->ctx->pending == e) { cudaStreamSynchronize(e->ctx->stream); e->ctx->pending = nullptr; }   // abandoned submit
     cudaFree(e->d_state[0]); cudaFree(e->d_state[1]);
     delete e;
 }
@@ -419,6 +421,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
 
 static int check_encode_args(zlb_encoder* e, const void* in, size_t n, const void* out, size_t* out_len) {
     if (!e || !out_len || (n && (!in || !out))) return fail(ZLB_E_ARG, "zlb_encode_blocks: null argument");
+    if (e->ctx->pending) return fail(ZLB_E_ARG, "zlb_encode_blocks: a submitted range is pending on this context (call zlb_encode_complete first)");
     if (n > (size_t) e->ctx->max_blocks * kBlockBytes) return fail(ZLB_E_ARG, "zlb_encode_blocks: more than max_blocks blocks in one call");
     return ZLB_OK;
 }
@@ -485,7 +488,7 @@ int zlb_encode_blocks(zlb_encoder* e, const uint8_t* in, size_t n, uint8_t* out,
 int zlb_encode_submit(zlb_encoder* e, const uint8_t* in, size_t n) {
     if (!e || (n && !in)) return fail(ZLB_E_ARG, "zlb_encode_submit: null argument");
     if (n == 0 || n > (size_t) e->ctx->max_blocks * kBlockBytes) return fail(ZLB_E_ARG, "zlb_encode_submit: size must be 1..max_blocks blocks");
-    if (e->submitted_n) return fail(ZLB_E_ARG, "zlb_encode_submit: a submit is already pending");
+    if (e->submitted_n || e->ctx->pending) return fail(ZLB_E_ARG, "zlb_encode_submit: a submit is already pending on this context");
     zlb_ctx* c = e->ctx;
     CU(cudaSetDevice(c->device));
     CU(cudaEventRecord(c->ev[EV_START], c->stream));
@@ -497,6 +500,7 @@ int zlb_encode_submit(zlb_encoder* e, const uint8_t* in, size_t n) {
     const int rc = encode_device(e, c->d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SUBMIT);
     if (rc) return rc;
     e->submitted_n = n;
+    c->pending = e;
     return ZLB_OK;
 }
 int zlb_encode_complete(zlb_encoder* e, uint8_t* out, size_t out_cap, size_t* out_len) {
@@ -506,6 +510,7 @@ int zlb_encode_complete(zlb_encoder* e, uint8_t* out, size_t out_cap, size_t* ou
     CU(cudaSetDevice(c->device));
     const size_t n = e->submitted_n;
     e->submitted_n = 0;
+    c->pending = nullptr;
     *out_len = 0;
     size_t produced = 0;
     int level_after = e->cur_level;
@@ -545,6 +550,7 @@ int zlb_debug_huff_tables(zlb_ctx* c, const uint32_t* freq, int ntables, int nsy
     CU(cudaSetDevice(c->device));
     uint32_t* d_f = nullptr; uint8_t* d_l = nullptr; uint16_t* d_c = nullptr;
     const size_t cnt = (size_t) ntables * nsym;
+    struct Free { uint32_t*& f; uint8_t*& l; uint16_t*& c; ~Free() { cudaFree(f); cudaFree(l); cudaFree(c); } } guard{ d_f, d_l, d_c };
     CU(cudaMalloc(&d_f, cnt * 4)); CU(cudaMalloc(&d_l, cnt)); CU(cudaMalloc(&d_c, cnt * 2));
     CU(cudaMemcpy(d_f, freq, cnt * 4, cudaMemcpyHostToDevice));
     zl_huff_tables_only_kernel<<<ntables, 256, 0, c->stream>>>(d_f, nsym, cap, d_l, d_c);
@@ -552,7 +558,6 @@ int zlb_debug_huff_tables(zlb_ctx* c, const uint32_t* freq, int ntables, int nsy
     CU(cudaGetLastError());
     CU(cudaMemcpy(len_out, d_l, cnt, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(code_out, d_c, cnt * 2, cudaMemcpyDeviceToHost));
-    cudaFree(d_f); cudaFree(d_l); cudaFree(d_c);
     return ZLB_OK;
 }
 
@@ -582,6 +587,7 @@ void zlb_decoder_end(zlb_decoder* d) {
 int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consumed, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!d || !consumed || !out_len || (n && !in)) return fail(ZLB_E_ARG, "zlb_decode_blocks: null argument");
     zlb_ctx* c = d->ctx;
+    if (c->pending) return fail(ZLB_E_ARG, "zlb_decode_blocks: a submitted encode range is pending on this context");
     CU(cudaSetDevice(c->device));
     *consumed = 0; *out_len = 0;
     if (n == 0) return ZLB_OK;
