@@ -66,6 +66,8 @@ int main(int argc, char** argv) {
     int nt = 0, nl = 0;
     for (int first = 0; first < 2; first++)
         if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(in[r.ip], 0, true); r.op++; r.ip++; }
+    std::vector<uint16_t> dump_flen((size_t) ilen + 600, 0);
+    std::vector<uint8_t> dump_mark((size_t) ilen + 600, 0);
     int s_level = r.level, s_tlevel[2] = { 0, 0 };
     const int lim = ilen - kGuard;
     const int nwin = lim > 2 ? (lim + kV3W - 1) / kV3W : 0;
@@ -80,6 +82,7 @@ int main(int argc, char** argv) {
         for (int rel = 0; rel < kV3W + 2; rel++) v3_spec_position(c, j, rel);
         for (int x = nlo; x < nhi; x++) v3_link_position(c, x, v3_base(j));
         for (int rel = 0; rel < kV3W; rel++) v3_decide_position(c, j, rel, tlevel);
+        for (int rel = 0; rel < kV3W && j * kV3W + rel < ilen; rel++) dump_flen[(size_t) j * kV3W + rel] = (uint16_t) (v3_table(c, j).dec[rel].x & 511u);
         s_tlevel[j & 1] = tlevel;
     };
     for (int k = -1; k < nwin; k++) {
@@ -93,6 +96,7 @@ int main(int argc, char** argv) {
                 const uint32_t m = c.ins[y & (kV3R - 1)];
                 if (!v3_kind(m)) continue;
                 v3_apply_position(c, y);
+                dump_mark[y] = (uint8_t) (v3_kind(m) | ((m & kInsExplicit) ? 8u : 0u));
                 c.tok[nt] = v3_token_of(c, y, m);
                 if (v3_kind(m) == kKindLit) c.lit[nl++] = (uint32_t) nt;
                 nt++;
@@ -107,6 +111,11 @@ int main(int argc, char** argv) {
     if (ilen > 0) v3_close_subblock(c, r, nt);
     const int nsub = ilen > 0 ? r.j + 1 : 0;
     const int sim_nt = nt;
+
+    if (getenv("ZL_V3_DUMP")) {                                        // analysis aid (scripts/chain_sync_stats.py)
+        FILE* df = fopen(getenv("ZL_V3_DUMP"), "wb");
+        if (df) { fwrite(dump_flen.data(), 2, ilen, df); fwrite(dump_mark.data(), 1, ilen, df); fclose(df); }
+    }
 
     // ---------------- oracle
     zo_rolz* z = zo_rolz_new();
