@@ -317,12 +317,12 @@ def main():
                        "bytes_per_gpu": int(nbytes), "level": args.level, "blocks_per_gpu": int(nblocks), "compressed_bytes": len(want),
                        "ratio": round(ratio, 4), "bit_exact_vs_cpu_reference": not args.skip_parity,
                        "l2": "256 MB buffer written between timed steps (L2 flush); working set (input + 12 MB bucket state/block + tokens) exceeds L2",
-                       "parse_kernel": "zl_rolz_parse_v%s" % os.environ.get("ZLB_PARSE", "3")},
+                       "parse_kernel": "zl_rolz_parse_v%s" % os.environ.get("ZLB_PARSE", "4")},
             "e2e": {"value": round(e2e_value, 3), "unit": "MB/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(len(want)),
                     "ms_per_step": round(e2e_step * 1e3, 3)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "zl_rolz_parse_v%s (one launch per step, 1 CTA per 16 MiB block)" % os.environ.get("ZLB_PARSE", "3"),
+            "roofline": {"bound": "hbm", "kernel": "zl_rolz_parse_v%s (one launch per step, 1 CTA per 16 MiB block)" % os.environ.get("ZLB_PARSE", "4"),
                          "achieved": round(ach, 4), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 6), "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
                          "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(nbytes),
                          "peak_source": peak_src,
@@ -331,7 +331,7 @@ def main():
             "kernel_ms": {"parse": round(pms, 3), "mtf": round(float(np.mean(mtf_ms)), 3), "huff_build": round(float(np.mean(build_ms)), 3),
                           "pack": round(float(np.mean(pack_ms)), 3), "wall_ms_per_step_incl_flush": round(wall_dev / args.steps * 1e3, 3)},
             "parse_counters": {k: int(last[k]) for k in ("tokens", "subblocks", "slow_main", "slow_lazy", "general_path", "window_hits", "windows", "reparsed_blocks",
-                                                          "cyc_spec", "cyc_resolve", "cyc_total", "flagged")},
+                                                          "cyc_spec", "cyc_resolve", "cyc_total", "flagged", "rounds", "cyc_final", "cyc_orbit", "cyc_rank", "cyc_decide")},
             "decode": decode,
             "cpu_baseline": {"value": round(nbytes / 1e6 / cpu_dt, 3), "unit": "MB/s", "cores": 1, "kind": cpu_kind,
                              "sample": "the whole %d-byte workload once, single thread (the reference codec has no threading); %d host cores present" % (nbytes, os.cpu_count())},

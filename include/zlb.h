@@ -124,6 +124,11 @@ typedef struct {
     uint64_t general_path;    /* parse: tokens resolved through the in-window candidate path instead of the frozen decision */
     uint64_t cyc_total;       /* parse v3: SM cycles from kernel start to end, summed over blocks */
     uint64_t flagged;         /* parse v3: tokens whose decision carried a hazard flag (checked; most stay frozen) */
+    uint64_t rounds;          /* parse v4: fixed-point rounds executed, summed over windows and blocks */
+    uint64_t cyc_final;       /* parse v4: SM cycles in FINALIZE (bucket writes, token emission), summed over blocks */
+    uint64_t cyc_orbit;       /* parse v4: SM cycles of the rounds spent on the orbit (pointer doubling) */
+    uint64_t cyc_rank;        /* parse v4: ... on the per-context ranks */
+    uint64_t cyc_decide;      /* parse v4: ... on re-deriving the decisions */
 } zlb_stats;
 int zlb_get_stats(const zlb_ctx* ctx, zlb_stats* out);
 

@@ -25,7 +25,8 @@ class Stats(C.Structure):
                 ("ms_pack", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double), ("launches", C.c_uint32),
                 ("parse_launches", C.c_uint32), ("reparsed_blocks", C.c_uint32), ("tokens", C.c_uint64), ("subblocks", C.c_uint64),
                 ("slow_main", C.c_uint64), ("slow_lazy", C.c_uint64), ("window_hits", C.c_uint64), ("windows", C.c_uint64),
-                ("cyc_spec", C.c_uint64), ("cyc_resolve", C.c_uint64), ("general_path", C.c_uint64), ("cyc_total", C.c_uint64), ("flagged", C.c_uint64)]
+                ("cyc_spec", C.c_uint64), ("cyc_resolve", C.c_uint64), ("general_path", C.c_uint64), ("cyc_total", C.c_uint64), ("flagged", C.c_uint64),
+                ("rounds", C.c_uint64), ("cyc_final", C.c_uint64), ("cyc_orbit", C.c_uint64), ("cyc_rank", C.c_uint64), ("cyc_decide", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(32) zl_rolz_parse_kernel(ParseArgs a) {
 }  // namespace zl
 #include "zl_parse_v2.cuh"
 #include "zl_parse_v3.cuh"
+#include "zl_parse_v4.cuh"
 namespace zl {
 
 // =====================================================================================================

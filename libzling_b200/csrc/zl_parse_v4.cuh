@@ -1,0 +1,1049 @@
+// zl_rolz_parse_v4 — the ROLZ parse as a data-parallel fixed-point iteration over windows of 1024 positions.
+//
+// The reference's parse (EncodeImpl + MatchAndUpdate + MatchLazy, src/libzling_lz.cpp:139-316) is one serial chain
+// per 16 MiB block: whether position p is a token start, and what the bucket holds when p is probed, depend on
+// every earlier decision.  v3 walked that chain with ONE thread per block (470 cycles per token).  v4 keeps v3's
+// exactness argument — records against a frozen bucket state G plus the inserts still pending in the window — and
+// replaces the walker with a Jacobi iteration in which every step is parallel over the window's positions:
+//
+//   SPEC      every position x of the window (one thread each): key, link to the nearest earlier same-key position
+//             of the window, the hash chain of x in G (G = all inserts before the window; up to dmax nodes with match
+//             lengths), and the decision the reference takes if no insert of this window interferes ("frozen").
+//   ROUNDS    state = one decision per position (kind, length).  Each round: (1) the token starts M are the orbit of
+//             the window's entry position under "next = x + step(decision)" (pointer doubling); (2) per-context
+//             ranks of the marked positions give every pending insert its ring slot; (3) every position re-derives
+//             its decision from M and the decisions: in-window candidates (marked same-key positions, newest first)
+//             merged with the frozen record in the reference's visiting order, ring slots overwritten since the
+//             freeze, the lazy probes at x+1 / x+2, the word-MRU state at x (folded from the pushes of the marked
+//             token ends), the sub-block roll-over.  The iteration stops when no marked position changed its
+//             decision: by induction over the token order the state is then exactly the reference's parse (the first
+//             token's decision depends on carried state only, every later one on earlier tokens only).
+//   FINALIZE  ring/hash writes of the window's inserts into G, token words and literal list from the marks (prefix
+//             sums), carried word-MRU / insert counters / symbol count.
+//
+// Every function of the algorithm is scalar ZL_HD code; tests/cxx/parse_v4_sim.cu replays the phases on the host
+// against the CPU checker (the GPU then has to confirm the kernel's synchronisation and its parallel forms of the
+// ordered passes: link building, ranks, orbit, prefix sums).
+#pragma once
+#include "zl_kernels.cuh"
+
+namespace zl {
+
+#ifndef ZL_V4_W
+#define ZL_V4_W 1024
+#endif
+constexpr int kV4W       = ZL_V4_W;             // main positions per window = threads per CTA
+constexpr int kV4N       = kV4W + 2;            // + two lazy look-ahead positions (records only)
+constexpr int kV4R       = 2048;                // byte ring: >= 4 + kV4N + 264 + 16
+constexpr int kV4Tail    = 288;                 // bytes staged past the last look-ahead position
+constexpr int kV4Buckets = 4096;                // buckets of the link builder
+constexpr int kV4Words   = (kV4W + 3 + 31) / 32;  // bitset words over window positions (+3: push contexts start 3 bytes early)
+constexpr uint32_t kV4KeyInvalid = 0x80000000u; // position cannot be probed (first two bytes / last 273 bytes of the block)
+constexpr uint32_t kV4KeyMask    = 0x1fffffu;   // (context << 13) | hash slot
+constexpr uint32_t kV4Auto       = 0xffu;       // plan entry: predict the level (see v4_next_level)
+
+// decision word: len(9) | kind(3) << 9 | match idx(12) << 12
+constexpr uint32_t kV4Match = 1, kV4Lit = 2, kV4Word0 = 3, kV4Word1 = 4;
+constexpr uint32_t kV4DecCmp = 0xfffu;          // the part of a decision that defines the parse (idx is derived)
+ZL_HD uint32_t v4_dec_len(uint32_t d)  { return d & 511u; }
+ZL_HD uint32_t v4_dec_kind(uint32_t d) { return (d >> 9) & 7u; }
+ZL_HD uint32_t v4_dec_idx(uint32_t d)  { return (d >> 12) & 0xfffu; }
+ZL_HD uint32_t v4_dec_step(uint32_t d) { const uint32_t k = v4_dec_kind(d); return k == kV4Match ? v4_dec_len(d) : (k == kV4Lit ? 1u : 2u); }
+ZL_HD uint32_t v4_dec_syms(uint32_t d) { return v4_dec_kind(d) == kV4Match ? 2u : 1u; }
+// fx word: frozen slot head (16) | flags << 16
+constexpr uint32_t kV4F_SELF = 1u << 16, kV4F_L1 = 1u << 17, kV4F_L2 = 1u << 18;
+
+// ---- portable intrinsics ---------------------------------------------------------------------------------------------
+ZL_HD uint32_t z4_funnel(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    sh &= 31u;
+    return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
+#endif
+}
+ZL_HD int z4_ffs(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int) v);
+#else
+    return __builtin_ffs((int) v);
+#endif
+}
+ZL_HD int z4_clz(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int) v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
+ZL_HD uint64_t z4_ld_ring(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));
+#else
+    return *p;
+#endif
+}
+ZL_HD uint32_t z4_ld_hash(const uint16_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+ZL_HD uint32_t z4_ld_in32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+ZL_HD uint4 z4_ld_in128(const uint4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// unaligned little-endian 32-bit load from the input block (global memory); `in` is 16-byte aligned
+ZL_HD uint32_t z4_in32(const uint8_t* in, uint32_t off) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(in) + (off >> 2);
+    return z4_funnel(z4_ld_in32(w), z4_ld_in32(w + 1), (off & 3u) * 8u);
+}
+ZL_HD uint32_t z4_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w >> 24) * 13337u; }   // lz.cpp:55-57
+
+// ---- shared-memory layout ----------------------------------------------------------------------------------------------
+struct V4Layout {
+    int dmax, lmax;
+    int rb, key, link, blink, llen, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
+    int scratch_bytes;
+};
+// scratch is a union: SPEC uses it for the link builder's bucket tables, the rounds for the orbit / rank tables
+constexpr int kV4Groups      = 8;                                          // link builder: position groups with their own bucket table
+constexpr int kV4Levels      = 11;                                         // orbit: jump tables J^(2^l), l < kV4Levels
+constexpr int kV4ScratchSpec = kV4Groups * kV4Buckets * 2;
+constexpr int kV4ScratchRnd  = kV4Levels * ((kV4N * 2 + 15) & ~15) + 33 * 256 * 2;
+__host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
+    V4Layout L; L.dmax = dmax; L.lmax = lmax;
+    int at = 0;
+    auto take = [&](int bytes) { int o = at; at += (bytes + 15) & ~15; return o; };
+    L.rb    = take(kV4R);
+    L.key   = take(4 * kV4N);
+    L.link  = take(2 * kV4N);
+    L.blink = take(2 * kV4N);
+    L.llen  = take(2 * kV4N);
+    L.hdr   = take(4 * kV4N);
+    L.node  = take(4 * kV4N * dmax);
+    L.nodeq = take(4 * kV4N * lmax);
+    L.fdec  = take(4 * kV4N);
+    L.fx    = take(4 * kV4N);
+    L.rank  = take(2 * kV4N);
+    L.mark  = take(kV4N + 2);
+    L.plit  = take(kV4N + 2);
+    L.sup   = take(kV4N + 2);
+    L.dec   = take(4 * kV4N);
+    L.ndec  = take(4 * kV4N);
+    L.occ   = take(4 * 256 * kV4Words);
+    L.mbits = take(4 * kV4Words);
+    L.cnt   = take(4 * 256);
+    L.mru   = take(4 * 256);
+    L.mru2  = take(4 * 256);
+    L.scratch_bytes = kV4ScratchSpec > kV4ScratchRnd ? kV4ScratchSpec : kV4ScratchRnd;
+    L.scratch = take(L.scratch_bytes);
+    L.total = at;
+    return L;
+}
+
+struct V4Ctx {
+    // block
+    const uint8_t* in; int ilen;
+    uint64_t* ring; uint16_t* hash;             // G: bucket state in global memory
+    uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
+    // shared memory (indexed by rel = x - lo unless noted)
+    uint32_t* rbw;                              // input bytes: ring of kV4R bytes viewed as words, indexed by block position
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* llen; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
+    uint32_t* fdec; uint32_t* fx; uint16_t* rank; uint8_t* mark; uint8_t* plit; uint8_t* sup; uint32_t* dec; uint32_t* ndec;
+    uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c)
+    uint32_t* mbits;                            // [kV4Words]: bit i <=> position lo + i is a token start
+    uint32_t* cnt; uint32_t* mru; uint32_t* mru2;   // carried: inserts per context before the window, word MRU at the window's entry
+    uint32_t* last;                             // host replay only: bucket table of the serial link builder
+    int dmax, lmax;
+};
+__host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
+    c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
+    c.blink = (uint16_t*) (smem + L.blink); c.llen = (uint16_t*) (smem + L.llen); c.hdr = (uint32_t*) (smem + L.hdr);
+    c.node = (uint32_t*) (smem + L.node); c.nodeq = (uint32_t*) (smem + L.nodeq); c.fdec = (uint32_t*) (smem + L.fdec);
+    c.fx = (uint32_t*) (smem + L.fx); c.rank = (uint16_t*) (smem + L.rank); c.mark = smem + L.mark; c.plit = smem + L.plit;
+    c.sup = smem + L.sup; c.dec = (uint32_t*) (smem + L.dec); c.ndec = (uint32_t*) (smem + L.ndec);
+    c.occ = (uint32_t*) (smem + L.occ); c.mbits = (uint32_t*) (smem + L.mbits);
+    c.cnt = (uint32_t*) (smem + L.cnt); c.mru = (uint32_t*) (smem + L.mru); c.mru2 = (uint32_t*) (smem + L.mru2);
+    c.last = nullptr;
+    c.dmax = L.dmax; c.lmax = L.lmax;
+}
+
+// per-window constants (uniform over the CTA)
+struct V4Win {
+    int lo, wend;            // window = positions [lo, lo + kV4W); tokens start at x < wend = min(lo + kV4W, ilen - kGuard)
+    int entry;               // first token start of the window (>= lo)
+    int level;               // level in force at the entry = level the frozen decisions assume
+    int rpos, level2;        // sub-block roll-over: the token at rpos opens a new sub-block parsed at level2 (rpos < 0: none)
+    int skip_push;           // the entry has no word-MRU push (block start: the two raw bytes push nothing)
+    int prev_lit;            // the token that ends at the entry is a literal
+};
+ZL_HD int v4_stage_hi(int k) { return (((k + 1) * kV4W + 2 + kV4Tail) + 15) & ~15; }   // bytes [.., hi) are staged once window k is prepared
+
+// ---- byte ring ---------------------------------------------------------------------------------------------------------
+ZL_HD uint32_t v4_rb32(const uint32_t* rbw, uint32_t pos) {          // unaligned LE 32-bit load at block position pos
+    const uint32_t i = (pos >> 2) & (kV4R / 4 - 1);
+    return z4_funnel(rbw[i], rbw[(i + 1) & (kV4R / 4 - 1)], (pos & 3u) * 8u);
+}
+ZL_HD uint32_t v4_rb8(const uint32_t* rbw, uint32_t pos) {
+    return (rbw[(pos >> 2) & (kV4R / 4 - 1)] >> ((pos & 3u) * 8u)) & 0xffu;
+}
+// stage 16 input bytes at block offset src (multiple of 16, may be negative or past the block: zeros)
+ZL_HD void v4_stage16(const V4Ctx& c, int src) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (src >= 0 && src < c.ilen) {
+        v = z4_ld_in128(reinterpret_cast<const uint4*>(c.in + src));
+        const int over = src + 16 - c.ilen;                              // bytes past the block end are staged as zeros
+        if (over > 0) {
+            uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            for (int b = 16 - over; b < 16; b++) w[b >> 2] &= ~(0xffu << ((b & 3) * 8));
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    uint32_t* d = c.rbw + (((uint32_t) src >> 2) & (kV4R / 4 - 1));
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+}
+
+// ---- SPEC A: key of a position --------------------------------------------------------------------------------------------
+ZL_HD uint32_t v4_key_of(const V4Ctx& c, int x) {
+    if (x < 2 || x + 273 >= c.ilen) return kV4KeyInvalid;
+    const uint32_t h = z4_hash(v4_rb32(c.rbw, (uint32_t) x));
+    const uint32_t ctx = v4_rb8(c.rbw, (uint32_t) x - 1);
+    return (ctx << 13) | (h & (kSlots - 1)) | (((h >> 13) & 0xffu) << 21);
+}
+ZL_HD uint32_t v4_ctx_of(uint32_t key) { return (key >> 13) & 0xffu; }
+ZL_HD uint32_t v4_bucket_of(uint32_t key) { return ((key & kV4KeyMask) * 2654435761u) >> 20; }   // 12 bits
+
+// ---- SPEC B: nearest earlier position of the window in the same bucket (host form; the kernel builds the same chains
+// with one bucket table per group of 128 positions) -----------------------------------------------------------------------
+inline void v4_bucket_pass_serial(const V4Ctx& c) {
+    for (int i = 0; i < kV4Buckets; i++) c.last[i] = 0;
+    for (int rel = 0; rel < kV4N; rel++) {
+        const uint32_t k = c.key[rel];
+        uint32_t d = 0;
+        if (!(k & kV4KeyInvalid)) {
+            const uint32_t b = v4_bucket_of(k);
+            const uint32_t prev = c.last[b];
+            if (prev != 0) d = (uint32_t) rel - (prev - 1);
+            c.last[b] = (uint32_t) rel + 1;
+        }
+        c.blink[rel] = (uint16_t) d;
+    }
+}
+
+// exact GetCommonLength (lz.cpp:66-89) with both operands inside the byte ring
+ZL_HD int v4_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q) {
+    if (v4_rb32(rbw, p) != v4_rb32(rbw, q)) return 0;
+    for (int n = 4; n < 256; n += 4) {
+        const uint32_t d = v4_rb32(rbw, p + n) ^ v4_rb32(rbw, q + n);
+        if (d) return n + ((z4_ffs(d) - 1) >> 3);
+    }
+    const uint32_t d = v4_rb32(rbw, p + 256) ^ v4_rb32(rbw, q + 256);
+    const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
+    return 256 + (t < 3 ? t : 3);
+}
+// the same with the candidate q read from global memory (q < x, anywhere in the block)
+ZL_HD int v4_common_len_mixed(const V4Ctx& c, uint32_t x, uint32_t q) {
+    if (v4_rb32(c.rbw, x) != z4_in32(c.in, q)) return 0;
+    for (int n = 4; n < 256; n += 4) {
+        const uint32_t d = v4_rb32(c.rbw, x + n) ^ z4_in32(c.in, q + n);
+        if (d) return n + ((z4_ffs(d) - 1) >> 3);
+    }
+    const uint32_t d = v4_rb32(c.rbw, x + 256) ^ z4_in32(c.in, q + 256);
+    const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
+    return 256 + (t < 3 ? t : 3);
+}
+
+// ---- SPEC C: nearest earlier position of the window with the same key, and the match length against it ---------------------
+ZL_HD void v4_link_position(const V4Ctx& c, int lo, int rel) {
+    const uint32_t k = c.key[rel];
+    uint32_t out = 0;
+    if (!(k & kV4KeyInvalid)) {
+        int y = rel;
+        uint32_t d = c.blink[rel];
+        while (d != 0) {
+            y -= (int) d;
+            if (((c.key[y] ^ k) & kV4KeyMask) == 0) { out = (uint32_t) (rel - y); break; }
+            d = c.blink[y];
+        }
+    }
+    c.link[rel] = (uint16_t) out;
+    c.llen[rel] = out ? (uint16_t) v4_common_len_ring(c.rbw, (uint32_t) (lo + rel), (uint32_t) (lo + rel) - out) : (uint16_t) 0;
+}
+
+// ---- SPEC D: chain record of a position against the frozen bucket state G -----------------------------------------------
+ZL_HD uint32_t v4_ring_dist(uint32_t slot, uint32_t head_at_freeze) {   // inserts into the context until `slot` is overwritten (1..4096)
+    return ((slot - head_at_freeze - 1u) & (kRing - 1)) + 1u;
+}
+// hdr[rel] = nodes recorded (5) | (smallest ring distance of a slot the walk read - 1) << 5
+// node[rel * dmax + i] = match length (0 if the check byte differs, lz.cpp:245) | ring slot << 9
+// nodeq[rel * lmax + i] = candidate position (the lazy probes compare 4 bytes at an offset only known later)
+ZL_HD void v4_spec_position(const V4Ctx& c, int lo, int rel) {
+    const int x = lo + rel;
+    const uint32_t k = c.key[rel];
+    if (k & kV4KeyInvalid) { c.hdr[rel] = (uint32_t) (kRing - 1) << 5; c.fx[rel] = (uint32_t) kNil; return; }
+    const uint32_t ctx = v4_ctx_of(k), slot = k & (kSlots - 1), chk = k >> 21;
+    const uint32_t head_b = c.cnt[ctx] & (kRing - 1);
+    const uint64_t* rc = c.ring + (size_t) ctx * kRing;
+    uint32_t node = z4_ld_hash(c.hash + (size_t) ctx * kSlots + slot);
+    c.fx[rel] = node;
+    uint32_t nvis = 0, dmin = kRing;
+    if (node != (uint32_t) kNil) {
+        dmin = v4_ring_dist(node, head_b);
+        uint64_t e = z4_ld_ring(rc + node);
+        for (int i = 0; i < c.dmax; i++) {
+            const uint32_t q = ring_pos(e);
+            const uint32_t nxt = ring_suffix(e);
+            // the next chain node is fetched while this one's bytes are compared (independent loads overlap)
+            const uint64_t e2 = nxt != (uint32_t) kNil ? z4_ld_ring(rc + nxt) : 0ull;
+            int len = 0;
+            if (ring_check(e) == chk) len = v4_common_len_mixed(c, (uint32_t) x, q);
+            c.node[rel * c.dmax + i] = (uint32_t) len | (node << 9);
+            if (i < c.lmax) c.nodeq[rel * c.lmax + i] = q;
+            nvis = i + 1;
+            if (nxt == (uint32_t) kNil) break;
+            dmin = min(dmin, v4_ring_dist(nxt, head_b));
+            if (q <= ring_pos(e2)) break;                                // lz.cpp:264
+            node = nxt; e = e2;
+        }
+    }
+    c.hdr[rel] = nvis | ((dmin - 1u) << 5);
+}
+
+// ---- SPEC E: the frozen decision of a main position ----------------------------------------------------------------------
+// fdec[rel] = flen(9) | fbest(9) << 9 | fslot(12) << 18: match length after the lazy veto / before it / ring slot of the best
+// node, all against G alone; fx[rel] gets the flags saying which of x, x+1, x+2 have an earlier same-key position in the window
+ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
+    const int x = lo + rel;
+    const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
+    const uint32_t hdr = c.hdr[rel];
+    const int nvis = (int) (hdr & 31u);
+    uint32_t fbest = 0, fslot = 0;
+    const int take = nvis < D ? nvis : D;
+    for (int i = 0; i < take; i++) {
+        const uint32_t nd = c.node[rel * c.dmax + i];
+        if ((nd & 511u) > fbest) { fbest = nd & 511u; fslot = nd >> 9; }
+    }
+    uint32_t flen = fbest >= (uint32_t) kMinLen ? fbest : 0u;
+    if (fbest < (uint32_t) kMinLen) fbest = 0;
+    const bool lazy_matters = fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow;
+    if (lazy_matters) {                                                  // lz.cpp:270-281 against G
+        const uint32_t at = fbest - 3u;
+        for (int which = 1; which <= 2 && flen; which++) {
+            const int depth = which == 1 ? L1 : L2;
+            const int nvx = (int) (c.hdr[rel + which] & 31u);
+            int tk = nvx < depth ? nvx : depth;
+            if (tk > c.lmax) tk = c.lmax;
+            const uint32_t mine = v4_rb32(c.rbw, (uint32_t) (x + which) + at);
+            for (int i = 0; i < tk; i++)
+                if (z4_in32(c.in, c.nodeq[(rel + which) * c.lmax + i] + at) == mine) flen = 0;
+        }
+    }
+    uint32_t fl = 0;
+    if (c.link[rel]) fl |= kV4F_SELF;
+    if (lazy_matters) {
+        if (c.link[rel + 1]) fl |= kV4F_L1;
+        if (c.link[rel + 2]) fl |= kV4F_L2;
+    }
+    c.fdec[rel] = flen | (fbest << 9) | (fslot << 18);
+    c.fx[rel] = (c.fx[rel] & 0xffffu) | fl;
+}
+
+// ---- ROUNDS: the pending view -----------------------------------------------------------------------------------------------
+// While position x (rel) is being decided the reference's bucket state is G plus the inserts of the marked positions
+// before x plus x's own insert (the insert precedes the search, lz.cpp:227-230).
+ZL_HD bool v4_pending(const V4Ctx& c, int xrel, int y) { return y == xrel || (y < xrel && c.mark[y] != 0); }
+ZL_HD uint32_t v4_head_of(const V4Ctx& c, int rel) {                    // ring slot of the insert made at rel
+    return (c.cnt[v4_ctx_of(c.key[rel])] + c.rank[rel] + 1u) & (kRing - 1);
+}
+// inserts into the context of position rel + q (q = 1, 2) made before and at rel
+ZL_HD uint32_t v4_cnt_lazy(const V4Ctx& c, int rel, int q) {
+    const uint32_t cw = v4_ctx_of(c.key[rel + q]);
+    uint32_t n = c.rank[rel + q];
+    for (int i = rel; i < rel + q; i++) if (c.mark[i] && v4_ctx_of(c.key[i]) == cw) n--;
+    if (v4_ctx_of(c.key[rel]) == cw) n++;
+    return n;
+}
+// is some same-key position before z, not after xrel, pending?
+ZL_HD bool v4_link_hazard(const V4Ctx& c, int z, int xrel, bool self_counts) {
+    int y = z;
+    while (true) {
+        const uint32_t d = c.link[y];
+        if (!d) return false;
+        y -= (int) d;
+        if (y > xrel) continue;
+        if (y == xrel) { if (self_counts) return true; continue; }
+        if (c.mark[y]) return true;
+    }
+}
+// Leading nodes of a record whose ring slots have not been overwritten after `kc` further inserts into the context.
+// A record node that HAS been overwritten ends the reference's walk right there when it is not the first one (the slot
+// now holds a newer, i.e. larger, position: the "offset <= next offset" test of lz.cpp:264 fires), so a record cut at
+// its first overwritten node is still exact; only an overwritten FIRST node needs the literal replay.
+ZL_HD int v4_valid_nodes(const V4Ctx& c, int rel, int nvis, uint32_t head_b, uint32_t kc) {
+    int i = 0;
+    while (i < nvis && v4_ring_dist(c.node[rel * c.dmax + i] >> 9, head_b) > kc) i++;
+    return i;
+}
+// slot head seen by the insert at y: the nearest marked same-key position before it, else the frozen head
+ZL_HD uint32_t v4_suffix_of(const V4Ctx& c, int y) {
+    int t = y;
+    while (true) {
+        const uint32_t d = c.link[t];
+        if (!d) break;
+        t -= (int) d;
+        if (c.mark[t]) return v4_head_of(c, t);
+    }
+    return c.fx[y] & 0xffffu;
+}
+// the reference's ring[ctx][n] as seen while xrel is decided
+ZL_HD uint64_t v4_live_entry(const V4Ctx& c, int lo, int xrel, uint32_t ctx, uint32_t n) {
+    const uint32_t ord = (n - c.cnt[ctx]) & (kRing - 1);
+    if (ord != 0 && ord <= (uint32_t) kV4N) {
+        for (int y = xrel; y >= 0; y--) {
+            if (!v4_pending(c, xrel, y)) continue;
+            const uint32_t k = c.key[y];
+            if ((k & kV4KeyInvalid) || v4_ctx_of(k) != ctx) continue;
+            if (v4_head_of(c, y) == n) return ring_make((uint32_t) (lo + y), k >> 21, v4_suffix_of(c, y));
+        }
+    }
+    return z4_ld_ring(c.ring + (size_t) ctx * kRing + n);
+}
+ZL_HD int v4_common_len_any(const V4Ctx& c, uint32_t x, uint32_t q) {     // both operands from global memory
+    if (z4_in32(c.in, x) != z4_in32(c.in, q)) return 0;
+    for (int n = 4; n < 256; n += 4) {
+        const uint32_t d = z4_in32(c.in, x + n) ^ z4_in32(c.in, q + n);
+        if (d) return n + ((z4_ffs(d) - 1) >> 3);
+    }
+    const uint32_t d = z4_in32(c.in, x + 256) ^ z4_in32(c.in, q + 256);
+    const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
+    return 256 + (t < 3 ? t : 3);
+}
+// literal replay of the candidate walk of MatchAndUpdate (lz.cpp:234-267) on the pending view
+ZL_HD int v4_main_live(const V4Ctx& c, int lo, int xrel, uint32_t node, uint32_t head, uint32_t chk, uint32_t ctx, int D, uint32_t* bestslot) {
+    if (node == (uint32_t) kNil || node == head) return 0;
+    int best = kMinLen - 1;
+    uint64_t e = v4_live_entry(c, lo, xrel, ctx, node);
+    for (int hop = 0; hop < D; hop++) {
+        const uint32_t cand = ring_pos(e);
+        if (ring_check(e) == chk) {
+            const int l = v4_common_len_any(c, (uint32_t) (lo + xrel), cand);
+            if (l > best) { best = l; *bestslot = node; if (best == kMaxLen) break; }
+        }
+        const uint32_t nxt = ring_suffix(e);
+        if (nxt == (uint32_t) kNil) break;
+        const uint64_t e2 = v4_live_entry(c, lo, xrel, ctx, nxt);
+        if (cand <= ring_pos(e2)) break;
+        node = nxt; e = e2;
+    }
+    return best;
+}
+// literal replay of MatchLazy (lz.cpp:291-316) at position zrel on the pending view of xrel
+ZL_HD bool v4_lazy_live(const V4Ctx& c, int lo, int xrel, int zrel, int best, int depth) {
+    const uint32_t k = c.key[zrel];
+    const uint32_t ctx = v4_ctx_of(k);
+    uint32_t node = c.fx[zrel] & 0xffffu;                                // hash[ctx][slot]: newest pending same-key insert, else G's
+    {
+        int y = zrel;
+        while (true) {
+            const uint32_t d = c.link[y];
+            if (!d) break;
+            y -= (int) d;
+            if (y <= xrel && v4_pending(c, xrel, y)) { node = v4_head_of(c, y); break; }
+        }
+    }
+    if (node == (uint32_t) kNil) return false;
+    const uint32_t at = (uint32_t) best - 3u;
+    const uint32_t mine = z4_in32(c.in, (uint32_t) (lo + zrel) + at);
+    uint64_t e = v4_live_entry(c, lo, xrel, ctx, node);
+    for (int hop = 0; hop < depth; hop++) {
+        const uint32_t cand = ring_pos(e);
+        if (z4_in32(c.in, cand + at) == mine) return true;
+        const uint32_t nxt = ring_suffix(e);
+        if (nxt == (uint32_t) kNil) break;
+        const uint64_t e2 = v4_live_entry(c, lo, xrel, ctx, nxt);
+        if (cand <= ring_pos(e2)) break;
+        e = e2;
+    }
+    return false;
+}
+
+// Does the frozen decision at rel NOT stand because of the inserts pending in the window?
+ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, uint32_t kc0, int L2) {
+    const uint32_t fbest = (fd >> 9) & 511u;
+    const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (L2 > 0 ? 2 : 1) : 0;
+    if ((fxw & kV4F_SELF) && v4_link_hazard(c, rel, rel, false)) return true;
+    if (nlazy >= 1 && (fxw & kV4F_L1) && v4_link_hazard(c, rel + 1, rel, true)) return true;
+    if (nlazy >= 2 && (fxw & kV4F_L2) && v4_link_hazard(c, rel + 2, rel, true)) return true;
+    const uint32_t ctx = v4_ctx_of(c.key[rel]);
+    const uint32_t h0 = c.hdr[rel];
+    if ((h0 & 31u) && (h0 >> 5) + 1u <= kc0 && v4_valid_nodes(c, rel, (int) (h0 & 31u), c.cnt[ctx] & (kRing - 1), kc0) < (int) (h0 & 31u)) return true;
+    for (int q = 1; q <= nlazy; q++) {
+        const uint32_t hw = c.hdr[rel + q];
+        if (!(hw & 31u)) continue;
+        const uint32_t cw = v4_ctx_of(c.key[rel + q]);
+        const uint32_t kc = v4_cnt_lazy(c, rel, q);
+        if ((hw >> 5) + 1u <= kc && v4_valid_nodes(c, rel + q, (int) (hw & 31u), c.cnt[cw] & (kRing - 1), kc) < (int) (hw & 31u)) return true;
+    }
+    return false;
+}
+
+// The full MatchAndUpdate (lz.cpp:211-289) at rel on the pending view: in-window candidates (newest first), then the
+// frozen record.  Returns the match length (0 = none) and the ring slot of the best candidate.
+ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t kc0, uint32_t head, uint32_t* bestslot_out) {
+    const int x = lo + rel;
+    const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
+    const uint32_t kx = c.key[rel];
+    const uint32_t chk = kx >> 21, ctx = v4_ctx_of(kx);
+    int best = kMinLen - 1, visited = 0;
+    uint32_t bestslot = 0, suffix = c.fx[rel] & 0xffffu;
+    bool done = false, have_suffix = false;
+    {
+        int y = rel;
+        while (true) {
+            const uint32_t dl = c.link[y];
+            if (!dl) break;
+            y -= (int) dl;
+            if (!c.mark[y]) continue;
+            if (!have_suffix) { suffix = v4_head_of(c, y); have_suffix = true; }
+            if (visited < D && !done) {
+                visited++;
+                if ((c.key[y] >> 21) == chk) {
+                    const int l = y == rel - (int) c.link[rel] ? (int) c.llen[rel] : v4_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) (lo + y));
+                    if (l > best) { best = l; bestslot = v4_head_of(c, y); if (best == kMaxLen) done = true; }
+                }
+            } else break;
+        }
+    }
+    const uint32_t hdr = c.hdr[rel];
+    int nvis = (int) (hdr & 31u);
+    bool stale0 = false;
+    if (nvis > 0 && (hdr >> 5) + 1u <= kc0) {
+        const int nv = v4_valid_nodes(c, rel, nvis, c.cnt[ctx] & (kRing - 1), kc0);
+        stale0 = nv == 0;
+        nvis = nv;
+    }
+    if (!done && visited < D && (nvis > 0 || stale0)) {
+        if (stale0) {                                                    // the record's first slot has been overwritten: replay literally
+            uint32_t bn = 0;
+            best = v4_main_live(c, lo, rel, suffix, head, chk, ctx, D, &bn);
+            bestslot = bn;
+        } else {
+            const int take = nvis < D - visited ? nvis : D - visited;
+            for (int i = 0; i < take; i++) {
+                const uint32_t nd = c.node[rel * c.dmax + i];
+                const int l = (int) (nd & 511u);
+                if (l > best) { best = l; bestslot = nd >> 9; if (best == kMaxLen) break; }
+            }
+        }
+    }
+    if (best < kMinLen) return 0;
+    if (best < kLazyBelow) {                                             // lz.cpp:270-281
+        const uint32_t at = (uint32_t) best - 3u;
+        for (int which = 1; which <= 2; which++) {
+            const int depth = which == 1 ? L1 : L2;
+            if (depth == 0) break;
+            const int relz = rel + which;
+            const uint32_t cz = v4_ctx_of(c.key[relz]);
+            const uint32_t hz = c.hdr[relz];
+            int nvz = (int) (hz & 31u);
+            const uint32_t kcz = v4_cnt_lazy(c, rel, which);
+            if (nvz > 0 && (hz >> 5) + 1u <= kcz) {                      // stale lazy record: cut it, or replay when its head is gone
+                nvz = v4_valid_nodes(c, relz, nvz, c.cnt[cz] & (kRing - 1), kcz);
+                if (nvz == 0) {
+                    if (v4_lazy_live(c, lo, rel, relz, best, depth)) return 0;
+                    continue;
+                }
+            }
+            const uint32_t mine = v4_rb32(c.rbw, (uint32_t) (lo + relz) + at);
+            int vis = 0;
+            int y = relz;
+            while (vis < depth) {                                        // pending same-key positions, newest first (rel itself included)
+                const uint32_t dl = c.link[y];
+                if (!dl) break;
+                y -= (int) dl;
+                if (!v4_pending(c, rel, y)) continue;
+                vis++;
+                if (v4_rb32(c.rbw, (uint32_t) (lo + y) + at) == mine) return 0;
+            }
+            int tk = nvz < depth - vis ? nvz : depth - vis;
+            if (tk > c.lmax) tk = c.lmax;
+            for (int i = 0; i < tk; i++)
+                if (z4_in32(c.in, c.nodeq[relz * c.lmax + i] + at) == mine) return 0;
+        }
+    }
+    *bestslot_out = bestslot;
+    return best;
+}
+
+// ---- ROUNDS: word MRU ---------------------------------------------------------------------------------------------------------
+// Every token that ENDS at e pushes the word in[e-2..e-1] into the MRU of context in[e-3] (lz.cpp:163-166,183-185,
+// 190-191): unconditionally after a literal, otherwise only when the front differs (a 256 hit changes nothing, a 257
+// hit always differs).  The state seen at x for context cq is the fold of the pushes at the marked positions e <= x
+// with in[e-3] == cq (bitset occ[cq] & mbits) over the carried state.  Returns w0 | w1 << 16.
+ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t cq) {
+    uint32_t base = c.mru[cq];
+    int elo = w.entry - w.lo + (w.skip_push ? 1 : 0);                     // pushes happen at marked e >= elo
+    if (w.rpos >= 0 && w.lo + xrel >= w.rpos) { base = 0; elo = w.rpos - w.lo + 1; }   // the MRU is zeroed when a sub-block opens (lz.cpp:147)
+    if (xrel < elo) return base;
+    const uint32_t* occ = c.occ + cq * kV4Words;
+    // pushes newest first: (a1,u1), (a2,u2), ...; the state is that after the newest EFFECTIVE push j: (a_j, front before j)
+    bool have = false;                // a push whose effectiveness is still unknown (needs the front before it)
+    uint32_t a = 0; bool u = false;
+    int wi = xrel >> 5;
+    uint32_t m = occ[wi] & c.mbits[wi] & (0xffffffffu >> (31 - (xrel & 31)));
+    const int wlo = elo >> 5;
+    while (true) {
+        if (wi == wlo) m &= 0xffffffffu << (elo & 31);
+        while (m) {
+            const int b = 31 - z4_clz(m);
+            m &= ~(1u << b);
+            const int e = wi * 32 + b;
+            const uint32_t xe = (uint32_t) (w.lo + e);
+            const uint32_t pw = (v4_rb8(c.rbw, xe - 2) << 8) | v4_rb8(c.rbw, xe - 1);
+            if (have) {                                                  // pw is the front before the pending push a
+                if (u || pw != a) return a | (pw << 16);
+                // the pending push was a no-op: the state is that after this (older) push
+            }
+            have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
+        }
+        if (wi == wlo) break;
+        wi--;
+        m = occ[wi] & c.mbits[wi];
+    }
+    if (!have) return base;
+    if (u || (base & 0xffffu) != a) return a | (base << 16);
+    return base;
+}
+
+// ---- ROUNDS: the decision of a position given the marks --------------------------------------------------------------------
+ZL_HD uint32_t v4_decide(const V4Ctx& c, const V4Win& w, int rel) {
+    const int x = w.lo + rel;
+    const int level = (w.rpos >= 0 && x >= w.rpos) ? w.level2 : w.level;
+    const uint32_t fd = c.fdec[rel], fxw = c.fx[rel];
+    const uint32_t kx = c.key[rel], ctx = v4_ctx_of(kx);
+    const uint32_t kc0 = (uint32_t) c.rank[rel] + 1u;
+    const uint32_t head = (c.cnt[ctx] + kc0) & (kRing - 1);
+    uint32_t len = fd & 511u, bestslot = (fd >> 18) & (kRing - 1);
+    if (level != w.level || v4_hazard(c, rel, fd, fxw, kc0, depth_lazy2(level))) {
+        uint32_t bs = 0;
+        len = (uint32_t) v4_probe_general(c, w.lo, rel, level, kc0, head, &bs);
+        bestslot = bs;
+    }
+    if (len) return len | (kV4Match << 9) | (((head - bestslot) & (kRing - 1)) << 12);
+    const uint32_t m = v4_mru_state(c, w, rel, ctx);                    // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
+    const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
+    const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
+    return kind << 9;
+}
+
+// ---- FINALIZE ---------------------------------------------------------------------------------------------------------------
+// marked position rel: find the slot head its insert replaces, and tell the previous owner of the slot that it has been superseded
+ZL_HD uint32_t v4_claim_slot(const V4Ctx& c, int rel) {
+    int t = rel;
+    while (true) {
+        const uint32_t d = c.link[t];
+        if (!d) break;
+        t -= (int) d;
+        if (c.mark[t]) { c.sup[t] = 1; return v4_head_of(c, t); }
+    }
+    return c.fx[rel] & 0xffffu;
+}
+ZL_HD void v4_apply_position(const V4Ctx& c, int lo, int rel, uint32_t suffix) {
+    const uint32_t k = c.key[rel];
+    const uint32_t ctx = v4_ctx_of(k), slot = k & (kSlots - 1), chk = k >> 21, head = v4_head_of(c, rel);
+    c.ring[(size_t) ctx * kRing + head] = ring_make((uint32_t) (lo + rel), chk, suffix);
+    if (!c.sup[rel]) c.hash[(size_t) ctx * kSlots + slot] = (uint16_t) head;
+}
+ZL_HD uint32_t v4_token_of(const V4Ctx& c, int lo, int rel) {
+    const uint32_t d = c.dec[rel], kind = v4_dec_kind(d);
+    if (kind == kV4Lit) return tok_literal(v4_rb8(c.rbw, (uint32_t) (lo + rel)), v4_rb8(c.rbw, (uint32_t) (lo + rel) - 1), false);
+    if (kind == kV4Word0) return tok_word(0);
+    if (kind == kV4Word1) return tok_word(1);
+    return tok_match(v4_dec_len(d), v4_dec_idx(d));
+}
+
+// ---- resolver state carried across windows ------------------------------------------------------------------------------------
+struct V4Run {
+    int ip, op, j, level, tok_begin, enc_begin;
+    int prev_lit;                    // the previous token was a literal (its word-MRU push is unconditional)
+    int skip_push;                   // no push is pending on arrival (block start: the two raw bytes push nothing)
+    int tail;                        // ip reached the last 275 bytes: the rest is done by v4_resolve_tail
+};
+// Level of sub-block j.  The reference derives it from the PREVIOUS sub-block's Huffman size (src/libzling.cpp:261-266:
+// olen / (consumed + 1) > 0.95 => level 0), which is not known during the parse (the literal ranks depend on MTF state
+// carried across blocks).  plan[j] is the host's word: a level it has verified, or kV4Auto = "predict": a sub-block
+// that is almost all single-byte symbols (consumed <= 1.125 x symbols) will not compress.  The host verifies every
+// level afterwards from the real sizes and re-parses from the first wrong one, so a wrong guess only costs time.
+ZL_HD int v4_next_level(const V4Ctx& c, int j, int consumed, int op) {
+    const uint32_t p = c.plan[j < kMaxSubPerBlock ? j : kMaxSubPerBlock - 1];
+    if (p != kV4Auto) return (int) p;
+    if (j == 0) return c.base_level;
+    return consumed <= op + (op >> 3) ? 0 : c.base_level;
+}
+ZL_HD void v4_close_subblock(const V4Ctx& c, const V4Run& r, int ip, int op, int nt) {
+    if (r.j < kMaxSubPerBlock) {
+        SubBlock sb; sb.tok_begin = (uint32_t) r.tok_begin; sb.tok_end = (uint32_t) nt; sb.enc_begin = (uint32_t) r.enc_begin;
+        sb.enc_end = (uint32_t) ip; sb.rlen = (uint32_t) op; sb.level = (uint32_t) r.level; sb.olen = 0; sb.bits_lo = 0;
+        c.sub[r.j] = sb;
+    }
+}
+// The last 275 bytes of the block (no probe, no insert: lz.cpp:158) and blocks shorter than that: plain serial
+// code, tokens written directly.  nt / nl = tokens / literals emitted so far.
+ZL_HD void v4_resolve_tail(const V4Ctx& c, V4Run& r, int* nt_io, int* nl_io) {
+    int nt = *nt_io, nl = *nl_io;
+    int ip = r.ip, op = r.op;
+    const uint8_t* in = c.in;
+    bool pending_push = !r.skip_push && ip >= 3;
+    while (ip < c.ilen) {
+        if (pending_push) {
+            const uint32_t c3 = in[ip - 3], w = ((uint32_t) in[ip - 2] << 8) | in[ip - 1];
+            const uint32_t m = c.mru[c3];
+            if (r.prev_lit || (m & 0xffffu) != w) c.mru[c3] = w | (m << 16);
+        }
+        pending_push = true;
+        if (op + 1 >= kSubSymbols) {                                     // sub-block full (lz.cpp:153): close it, open the next
+            v4_close_subblock(c, r, ip, op, nt);
+            const int next = v4_next_level(c, r.j + 1, ip - r.enc_begin, op);
+            r.j++; r.level = next;
+            for (int i = 0; i < 256; i++) c.mru[i] = 0;                  // lz.cpp:147
+            op = 0; r.tok_begin = nt; r.enc_begin = ip;
+        }
+        const uint32_t c1 = in[ip - 1], cur = in[ip];
+        if (ip + 1 < c.ilen) {
+            const uint32_t w = (cur << 8) | in[ip + 1];
+            const uint32_t m = c.mru[c1];
+            if ((m & 0xffffu) == w) { c.tok[nt++] = tok_word(0); op++; ip += 2; r.prev_lit = 0; continue; }
+            if ((m >> 16) == w) { c.tok[nt++] = tok_word(1); op++; ip += 2; r.prev_lit = 0; continue; }
+        }
+        c.tok[nt] = tok_literal(cur, c1, false);
+        c.lit[nl++] = (uint32_t) nt;
+        nt++; op++; ip++; r.prev_lit = 1;
+    }
+    r.ip = ip; r.op = op;
+    *nt_io = nt; *nl_io = nl;
+}
+
+}  // namespace zl
+
+#if defined(__CUDACC__)
+namespace zl {
+
+struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide; };
+
+__device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
+
+// ---- the kernel: grid = blocks of the batch, kV4W threads, thread t owns position lo + t of the current window -----------
+__global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int dmax, int lmax, int base_level, V4Counters* counters) {
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!a.active[b]) return;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ V4Run s_run;
+    __shared__ V4Win s_win;
+    __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos, s_syms, s_syms_after;
+    __shared__ int s_wtok[kV4W / 32], s_wlit[kV4W / 32], s_wsym[kV4W / 32];
+    const V4Layout L = v4_layout(dmax, lmax);
+    V4Ctx c;
+    v4_bind(c, smem_raw, L);
+    c.in = a.in + (size_t) b * kBlockBytes; c.ilen = (int) a.ilen[b];
+    c.ring = a.ring + (size_t) b * kRingStride; c.hash = a.hash + (size_t) b * kHashStride;
+    c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
+    c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock; c.base_level = base_level;
+    const int ilen = c.ilen;
+    uint8_t* scratch = smem_raw + L.scratch;
+    uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
+    constexpr int kJStride = (kV4N * 2 + 15) & ~15;
+    uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + kV4Levels * kJStride);   // ROUNDS: [33][256] marked positions per (warp, context)
+    auto J = [&](int l) { return reinterpret_cast<uint16_t*>(scratch + l * kJStride); };
+
+    for (int i = tid; i < 256; i += kV4W) { c.cnt[i] = 0; c.mru[i] = 0; }
+    long long cyc_spec = 0, cyc_rounds = 0, cyc_final = 0, cyc_orbit = 0, cyc_rank = 0, cyc_decide = 0;
+    unsigned long long n_rounds = 0, n_windows = 0;
+    const long long t_begin = clock64();
+    if (tid == 0) {
+        V4Run r;
+        r.ip = 0; r.op = 0; r.j = 0; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
+        r.level = v4_next_level(c, 0, 0, 0);
+        int nt = 0;
+        for (int first = 0; first < 2; first++) {                        // first two bytes raw, lz.cpp:150-151
+            if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(c.in[r.ip], 0, true); r.op++; r.ip++; }
+        }
+        s_run = r; s_nt = nt; s_nl = 0;
+    }
+    __syncthreads();
+    const int lim = ilen - kGuard;
+    const int nwin = lim > 2 ? (lim + kV4W - 1) / kV4W : 0;              // windows that contain probe positions
+    int staged_hi = -16;
+
+    for (int k = 0; k < nwin; k++) {
+        const int lo = k * kV4W;
+        const int wend = lo + kV4W < lim ? lo + kV4W : lim;
+        const int Wn = wend - lo;
+        const int hi = v4_stage_hi(k);
+        for (int src = staged_hi + tid * 16; src < hi; src += kV4W * 16) v4_stage16(c, src);
+        staged_hi = hi;
+        __syncthreads();
+        if (s_run.ip >= wend) continue;                                  // no token starts in this window (uniform)
+        const long long t0 = clock64();
+        // ================================================= SPEC =================================================
+        c.key[tid] = v4_key_of(c, lo + tid);
+        if (tid < 2) c.key[kV4W + tid] = v4_key_of(c, lo + kV4W + tid);
+        for (int i = tid; i < 256 * kV4Words; i += kV4W) c.occ[i] = 0;
+        { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4W) z[i] = make_uint4(0, 0, 0, 0); }
+        __syncthreads();
+        {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..2 also bits W..W+2
+            const int p = lo + tid - 3;
+            const uint32_t v = p >= 0 ? v4_rb8(c.rbw, (uint32_t) p) : 256u + (uint32_t) lane;
+            const uint32_t grp = __match_any_sync(0xffffffffu, v);
+            if (p >= 0 && (grp >> lane) == 1u) c.occ[v * kV4Words + warp] = grp;
+            if (tid < 3) { const int p2 = lo + kV4W + tid - 3; atomicOr(&c.occ[v4_rb8(c.rbw, (uint32_t) p2) * kV4Words + (kV4W >> 5)], 1u << tid); }
+        }
+        v4_spec_position(c, lo, tid);                                    // chain records against G (global-memory latency lives here)
+        if (tid < 2) v4_spec_position(c, lo, kV4W + tid);
+        {   // link builder: nearest earlier position of the window in the same bucket.  Groups of 4 warps own a bucket table;
+            // inside a group the warps take turns in position order, then positions without a predecessor in their own
+            // group look at the final tables of the groups before theirs.
+            const int g = warp >> 2, turn = warp & 3;
+            uint16_t* tg = gtab + g * kV4Buckets;
+            const uint32_t kx = c.key[tid];
+            const bool valid = !(kx & kV4KeyInvalid);
+            const uint32_t bk = valid ? v4_bucket_of(kx) : 0xffff0000u + (uint32_t) lane;
+            uint32_t dist = 0;
+            for (int i = 0; i < 4; i++) {
+                if (turn == i) {
+                    const uint32_t grp = __match_any_sync(0xffffffffu, bk);
+                    const uint32_t lower = grp & v4_lt_mask(lane);
+                    if (valid) {
+                        if (lower) dist = (uint32_t) lane - (31u - (uint32_t) __clz(lower));
+                        else { const uint32_t prev = tg[bk]; if (prev) dist = (uint32_t) tid - (prev - 1u); }
+                    }
+                    __syncwarp();
+                    if (valid && (grp >> lane) == 1u) tg[bk] = (uint16_t) (tid + 1);
+                }
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory");
+            }
+            __syncthreads();
+            if (valid && dist == 0) {
+                for (int g2 = g - 1; g2 >= 0; g2--) {
+                    const uint32_t prev = gtab[g2 * kV4Buckets + bk];
+                    if (prev) { dist = (uint32_t) tid - (prev - 1u); break; }
+                }
+            }
+            c.blink[tid] = (uint16_t) dist;
+            if (tid == 0) {                                              // the two look-ahead positions
+                for (int rel = kV4W; rel < kV4N; rel++) {
+                    const uint32_t k2 = c.key[rel];
+                    uint32_t d2 = 0;
+                    if (!(k2 & kV4KeyInvalid)) {
+                        const uint32_t b2 = v4_bucket_of(k2);
+                        if (rel == kV4W + 1 && !(c.key[kV4W] & kV4KeyInvalid) && v4_bucket_of(c.key[kV4W]) == b2) d2 = 1;
+                        for (int g2 = kV4Groups - 1; g2 >= 0 && !d2; g2--) {
+                            const uint32_t prev = gtab[g2 * kV4Buckets + b2];
+                            if (prev) d2 = (uint32_t) rel - (prev - 1u);
+                        }
+                    }
+                    c.blink[rel] = (uint16_t) d2;
+                }
+            }
+        }
+        __syncthreads();
+        v4_link_position(c, lo, tid);
+        if (tid < 2) v4_link_position(c, lo, kV4W + tid);
+        __syncthreads();
+        const int wlevel = s_run.level;
+        v4_frozen_position(c, lo, tid, wlevel);
+        if (tid == 0) {
+            V4Win w; w.lo = lo; w.wend = wend; w.entry = s_run.ip; w.level = wlevel; w.rpos = -1; w.level2 = wlevel;
+            w.skip_push = s_run.skip_push; w.prev_lit = s_run.prev_lit;
+            s_win = w;
+        }
+        { const uint32_t fl = c.fdec[tid] & 511u; c.dec[tid] = fl ? (fl | (kV4Match << 9)) : (kV4Lit << 9); }
+        if (tid < 2) { c.dec[kV4W + tid] = kV4Lit << 9; c.mark[kV4W + tid] = 0; c.plit[kV4W + tid] = 0; }
+        if (tid == 0) c.mbits[kV4W >> 5] = 0;
+        __syncthreads();
+        const long long t1 = clock64();
+        cyc_spec += t1 - t0;
+        // ================================================= ROUNDS ===============================================
+        const int entry_rel = s_win.entry - lo;
+        const bool may_roll = s_run.op + 2 * kV4N + 1 >= kSubSymbols;
+        while (true) {
+            n_rounds++;
+            const long long r0 = clock64();
+            // ---- orbit of the entry under next = x + step(decision): pointer doubling
+            const uint32_t mydec = c.dec[tid];
+            { uint32_t t = tid < Wn ? (uint32_t) tid + v4_dec_step(mydec) : (uint32_t) Wn; if (t > (uint32_t) Wn) t = (uint32_t) Wn;
+              J(0)[tid] = (uint16_t) t; if (tid < 2) J(0)[kV4W + tid] = (uint16_t) Wn; }
+            c.mark[tid] = tid == entry_rel;
+            c.plit[tid] = 0;
+            __syncthreads();
+            int nlev = 1;
+            for (; nlev < kV4Levels - 1; nlev++) {
+                if (J(nlev - 1)[entry_rel] >= Wn) break;                 // 2^(nlev-1) steps leave the window: enough levels
+                const uint16_t* jp = J(nlev - 1);
+                J(nlev)[tid] = jp[jp[tid]];
+                if (tid < 2) J(nlev)[kV4W + tid] = (uint16_t) Wn;
+                __syncthreads();
+            }
+            for (int l = nlev - 1; l >= 0; l--) {
+                if (c.mark[tid]) { const int t = J(l)[tid]; if (t < Wn) c.mark[t] = 1; }
+                __syncthreads();
+            }
+            const bool marked = c.mark[tid] != 0;
+            if (marked) {
+                const int t = (int) tid + (int) v4_dec_step(mydec);
+                if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
+                else { s_exit = lo + t; s_lastrel = tid; }
+            }
+            { const uint32_t mb = __ballot_sync(0xffffffffu, marked); if (lane == 0) c.mbits[warp] = mb; }
+            // ---- per-context ranks of the marked positions
+            reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
+            if (tid == 0) { s_rpos_rel = 0x7fffffff; }
+            __syncthreads();
+            const long long r1 = clock64();
+            const uint32_t kx = c.key[tid];
+            const bool valid = !(kx & kV4KeyInvalid);
+            const uint32_t ctx = v4_ctx_of(kx);
+            uint32_t inwarp = 0;
+            {
+                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? ctx : 256u + (uint32_t) lane);
+                const uint32_t mk = __ballot_sync(0xffffffffu, marked);
+                inwarp = (uint32_t) __popc(grp & mk & v4_lt_mask(lane));
+                if (valid && (grp >> lane) == 1u) wcnt[warp * 256 + ctx] = (uint16_t) __popc(grp & mk);
+            }
+            // sub-block roll-over (rare): symbols before each marked position
+            if (may_roll) {
+                const uint32_t mysym = marked ? v4_dec_syms(mydec) : 0u;
+                uint32_t incl = mysym;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                if (lane == 31) s_wsym[warp] = (int) incl;
+                __syncthreads();
+                int before = s_run.op;
+                for (int w2 = 0; w2 < warp; w2++) before += s_wsym[w2];
+                before += (int) (incl - mysym);
+                if (marked && before + 1 >= kSubSymbols) atomicMin(&s_rpos_rel, tid);
+                __syncthreads();
+                if (s_rpos_rel == tid) s_op_at_rpos = before;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t run = 0;
+                #pragma unroll 8
+                for (int w2 = 0; w2 < 32; w2++) { const uint32_t t = wcnt[w2 * 256 + tid]; wcnt[w2 * 256 + tid] = (uint16_t) run; run += t; }
+                wcnt[32 * 256 + tid] = (uint16_t) run;
+            }
+            if (tid == 0) {
+                V4Win w = s_win;
+                w.rpos = -1; w.level2 = w.level;
+                if (may_roll && s_rpos_rel != 0x7fffffff) {
+                    w.rpos = lo + s_rpos_rel;
+                    w.level2 = v4_next_level(c, s_run.j + 1, w.rpos - s_run.enc_begin, s_op_at_rpos);
+                }
+                s_win = w;
+            }
+            __syncthreads();
+            c.rank[tid] = valid ? (uint16_t) (wcnt[warp * 256 + ctx] + inwarp) : (uint16_t) 0;
+            if (tid < 2) { const uint32_t k2 = c.key[kV4W + tid]; c.rank[kV4W + tid] = (k2 & kV4KeyInvalid) ? (uint16_t) 0 : wcnt[32 * 256 + v4_ctx_of(k2)]; }
+            __syncthreads();
+            const long long r2 = clock64();
+            // ---- every position re-derives its decision
+            const V4Win w = s_win;
+            uint32_t nd = mydec;
+            if (tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid);
+            const int changed = __syncthreads_or(marked && ((nd ^ mydec) & kV4DecCmp) != 0);
+            c.dec[tid] = nd;
+            const long long r3 = clock64();
+            cyc_orbit += r1 - r0; cyc_rank += r2 - r1; cyc_decide += r3 - r2;
+            if (!changed) break;
+            __syncthreads();
+        }
+        __syncthreads();
+        const long long t2 = clock64();
+        cyc_rounds += t2 - t1;
+        n_windows++;
+        // ================================================= FINALIZE =============================================
+        {
+            const V4Win w = s_win;
+            const bool marked = c.mark[tid] != 0;
+            const uint32_t d = c.dec[tid];
+            c.sup[tid] = 0;
+            __syncthreads();
+            uint32_t suffix = 0;
+            if (marked) suffix = v4_claim_slot(c, tid);
+            __syncthreads();
+            if (marked) v4_apply_position(c, lo, tid, suffix);
+            const bool islit = marked && v4_dec_kind(d) == kV4Lit;
+            const uint32_t bt = __ballot_sync(0xffffffffu, marked), bl = __ballot_sync(0xffffffffu, islit);
+            const bool after = w.rpos >= 0 && lo + tid >= w.rpos;
+            uint32_t sy = marked ? v4_dec_syms(d) : 0u;
+            uint32_t sya = after ? sy : 0u;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, o); sya += __shfl_xor_sync(0xffffffffu, sya, o); }
+            if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); s_wsym[warp] = (int) (sy | (sya << 16)); }
+            if (tid < 256) c.mru2[tid] = v4_mru_state(c, w, Wn - 1, (uint32_t) tid);
+            __syncthreads();
+            int tb = s_nt, lb = s_nl, ttot = 0, ltot = 0, stot = 0, satot = 0;
+            for (int w2 = 0; w2 < kV4W / 32; w2++) {
+                const int tw = s_wtok[w2], lw = s_wlit[w2];
+                if (w2 < warp) { tb += tw; lb += lw; }
+                ttot += tw; ltot += lw; stot += s_wsym[w2] & 0xffff; satot += s_wsym[w2] >> 16;
+            }
+            if (marked) {
+                const int ti = tb + __popc(bt & v4_lt_mask(lane));
+                c.tok[ti] = v4_token_of(c, lo, tid);
+                if (islit) c.lit[lb + __popc(bl & v4_lt_mask(lane))] = (uint32_t) ti;
+                if (w.rpos >= 0 && lo + tid == w.rpos) s_rpos_nt = ti;
+            }
+            if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += wcnt[32 * 256 + tid]; }
+            __syncthreads();
+            if (tid == 0) {
+                V4Run r = s_run;
+                if (w.rpos >= 0) {                                       // sub-block full (lz.cpp:153): close it, open the next
+                    v4_close_subblock(c, r, w.rpos, s_op_at_rpos, s_rpos_nt);
+                    r.j++; r.level = w.level2; r.tok_begin = s_rpos_nt; r.enc_begin = w.rpos;
+                    r.op = satot;
+                } else {
+                    r.op += stot;
+                }
+                r.ip = s_exit; r.skip_push = 0; r.prev_lit = v4_dec_kind(c.dec[s_lastrel]) == kV4Lit;
+                s_run = r; s_nt += ttot; s_nl += ltot;
+            }
+        }
+        __syncthreads();
+        cyc_final += clock64() - t2;
+    }
+    if (tid == 0) {
+        V4Run r = s_run;
+        r.tail = 1;
+        int nt = s_nt, nl = s_nl;
+        v4_resolve_tail(c, r, &nt, &nl);
+        if (ilen > 0) v4_close_subblock(c, r, r.ip, r.op, nt);
+        a.nsub[b] = ilen > 0 ? r.j + 1 : 0; a.ntok[b] = nt; a.nlit[b] = nl;
+        if (counters) {
+            atomicAdd(&counters->tokens, (unsigned long long) nt);
+            atomicAdd(&counters->windows, n_windows);
+            atomicAdd(&counters->rounds, n_rounds);
+            atomicAdd(&counters->cyc_spec, (unsigned long long) cyc_spec);
+            atomicAdd(&counters->cyc_rounds, (unsigned long long) cyc_rounds);
+            atomicAdd(&counters->cyc_final, (unsigned long long) cyc_final);
+            atomicAdd(&counters->cyc_orbit, (unsigned long long) cyc_orbit);
+            atomicAdd(&counters->cyc_rank, (unsigned long long) cyc_rank);
+            atomicAdd(&counters->cyc_decide, (unsigned long long) cyc_decide);
+            atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));
+        }
+    }
+}
+
+}  // namespace zl
+#endif
