@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "zl_kernels.cuh"
+#include "zl_mtf_walk.h"
 
 namespace zl {
 
@@ -395,12 +396,13 @@ __global__ void __launch_bounds__(kLitWarps * 32) zl_lit_scatter_kernel(const ui
 constexpr int kMtfChunk = 256;                                    // literal records staged per round
 
 // grid 256 (one CTA = one warp per context).  Lane 0 walks the context's literal list of every block in stream
-// order (ZlingMTFEncoder::Encode, lz.cpp:112-117); all lanes prefetch the next records into shared memory.
+// order (ZlingMTFEncoder::Encode, lz.cpp:112-117; the walk itself is mtf_walk, zl_mtf_walk.h: one dependent
+// shared-memory load per literal); all lanes prefetch the next records into shared memory and write the token words.
 __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const uint32_t* lbuf_all, const uint32_t* ctx_off, int first_block, int nblocks,
                                                         const uint8_t* state_in, uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
     const int ctx = blockIdx.x, lane = threadIdx.x;
     __shared__ __align__(16) uint8_t s_sym[256];          // rank -> byte
-    __shared__ __align__(16) uint8_t s_rank[256];         // byte -> rank
+    __shared__ __align__(16) uint16_t s_R[256];           // byte -> rank | mtf_next(rank) << 8
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
     __shared__ __align__(16) uint8_t s_out[kMtfChunk];
     __shared__ __align__(16) uint8_t s_byte[2][kMtfChunk + 16];
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
         const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
         for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
         __syncwarp();
-        for (int i = lane; i < 256; i += 32) s_rank[s_sym[i]] = (uint8_t) i;
+        for (int i = lane; i < 256; i += 32) s_R[s_sym[i]] = (uint16_t) (i | (mtf_next(i) << 8));
         __syncwarp();
     }
     for (int b = first_block; b < nblocks; b++) {
@@ -432,48 +434,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
             for (int q = 0; q < kMtfChunk / 32; q++) { const int i = base + kMtfChunk + q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
             __syncwarp();
             const int cnt = min(kMtfChunk, n - base);
-            if (lane == 0) {
-                // Two literals per step: the second one's table reads are issued together with the first one's and
-                // patched from registers where the first literal's swap touches them (the swap moves two entries).
-                // Bytes come four at a time (prefetched one step ahead), ranks leave four at a time; the token
-                // words are written by all lanes after the chunk.
-                #define ZL_MTF_PAIR(bA, bB, rA, rB) {                                                              \
-                    const int iA = s_rank[bA], iBr = s_rank[bB];                                                  \
-                    const int jA = s_next[iA];                                                                    \
-                    int iB = bB == bA ? jA : iBr;                       /* assumes bB is not the byte A swaps with */ \
-                    int jB = s_next[iB];                                                                          \
-                    const uint32_t oA = s_sym[jA];                                                                \
-                    uint32_t oBr = s_sym[jB];                                                                     \
-                    if (bB == oA && bB != bA) { iB = iA; jB = s_next[iB]; oBr = s_sym[jB]; }                      \
-                    const uint32_t oB = jB == iA ? oA : (jB == jA ? bA : oBr);                                    \
-                    s_sym[iA] = (uint8_t) oA; s_sym[jA] = (uint8_t) bA;                                           \
-                    s_rank[oA] = (uint8_t) iA; s_rank[bA] = (uint8_t) jA;                                         \
-                    s_sym[iB] = (uint8_t) oB; s_sym[jB] = (uint8_t) bB;                                           \
-                    s_rank[oB] = (uint8_t) iB; s_rank[bB] = (uint8_t) jB;                                         \
-                    rA = (uint32_t) iA; rB = (uint32_t) iB; }
-                int q = 0;
-                const uint32_t* byte4 = reinterpret_cast<const uint32_t*>(s_byte[buf]);
-                uint32_t* out4 = reinterpret_cast<uint32_t*>(s_out);
-                uint32_t nb4 = byte4[0];
-                for (; q + 3 < cnt; q += 4) {
-                    const uint32_t b4 = nb4;
-                    nb4 = byte4[(q >> 2) + 1];
-                    const uint32_t b0 = b4 & 0xffu, b1 = (b4 >> 8) & 0xffu, b2 = (b4 >> 16) & 0xffu, b3 = b4 >> 24;
-                    uint32_t r0, r1, r2, r3;
-                    ZL_MTF_PAIR(b0, b1, r0, r1)
-                    ZL_MTF_PAIR(b2, b3, r2, r3)
-                    out4[q >> 2] = r0 | (r1 << 8) | (r2 << 16) | (r3 << 24);
-                }
-                #undef ZL_MTF_PAIR
-                for (; q < cnt; q++) {
-                    const uint32_t byte = s_byte[buf][q];
-                    const int i = s_rank[byte], jn = s_next[i];
-                    const uint32_t other = s_sym[jn];
-                    s_sym[i] = (uint8_t) other; s_sym[jn] = (uint8_t) byte;
-                    s_rank[other] = (uint8_t) i; s_rank[byte] = (uint8_t) jn;
-                    s_out[q] = (uint8_t) i;
-                }
-            }
+            if (lane == 0) mtf_walk(s_R, s_sym, s_next, s_byte[buf], s_out, cnt);   // the serial chain: zl_mtf_walk.h
             __syncwarp();
             for (int q = lane; q < cnt; q += 32) {
                 const uint32_t rec = s_rec[buf][q];
