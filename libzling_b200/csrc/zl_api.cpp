@@ -11,6 +11,8 @@
 // block at a time because a handler may read from the Inputter inside OnProcess (demo/zling.cpp:124-132).
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -63,12 +65,22 @@ size_t FileOutputter::PutData(unsigned char* buf, size_t len) {
 bool FileOutputter::IsErr() { return ferror(m_fp) != 0; }
 size_t FileOutputter::GetOutputSize() { return m_total_write; }
 
-// ---- process-wide GPU context ---------------------------------------------------------------------------------
+// ---- GPU contexts: a small pool, one context per call in flight -------------------------------------------------
+// The reference's Encode/Decode are re-entrant (every call owns its EncodeResource/DecodeResource,
+// src/libzling.cpp:108-163,180,299); so are these: a call takes a context (device buffers + page-locked staging)
+// out of the pool for its whole duration and puts it back on every exit path; concurrent calls get different
+// contexts.  Two sizes exist: a 1-block context (about 260 MB of device memory, 33 MB page-locked) serves inputs
+// of up to 16 MiB, a ZLING_B200_BLOCKS-block one (default 8; about 2 GB / 260 MB) everything longer, so that a
+// small input never pays for the large buffers.  ZLING_B200_DEVICE selects the GPU.
 namespace {
 
-int env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt, int lo, int hi) {
     const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
+    if (!v || !*v) return dflt;
+    char* end = nullptr;
+    const long x = strtol(v, &end, 10);
+    if (end == v || *end != 0 || x < lo || x > hi) return dflt;          // unparsable or out of range: keep the default
+    return (int) x;
 }
 
 struct Gpu {
@@ -83,20 +95,52 @@ struct Gpu {
     }
 };
 
-Gpu& gpu() {
-    static Gpu g;      // one call at a time per process, like the reference's single-threaded use
-    if (!g.ctx) {
-        g.max_blocks = env_int("ZLING_B200_BLOCKS", 8);
-        g.ctx = zlb_create(env_int("ZLING_B200_DEVICE", 0), g.max_blocks);
-        if (!g.ctx) throw std::runtime_error(std::string("libzling (B200): ") + zlb_last_error());
-        g.in_cap = (size_t) g.max_blocks * ZLB_BLOCK_BYTES;
-        g.out_cap = zlb_encode_bound(g.in_cap);
-        g.pin_in = (unsigned char*) zlb_host_alloc(g.in_cap + 64);
-        g.pin_out = (unsigned char*) zlb_host_alloc(g.out_cap + 64);
-        if (!g.pin_in || !g.pin_out) throw std::bad_alloc();
+class Pool {
+public:
+    // a context able to hold `blocks` blocks (1 = the small tier, anything else = the large tier)
+    Gpu* acquire(bool large) {
+        const int want = large ? env_int("ZLING_B200_BLOCKS", 8, 1, 64) : 1;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            for (size_t i = 0; i < free_.size(); i++) {
+                if (free_[i]->max_blocks == want) { Gpu* g = free_[i]; free_.erase(free_.begin() + (long) i); return g; }
+            }
+        }
+        // build everything in a local object and hand it out only when all of it exists
+        std::unique_ptr<Gpu> g(new Gpu());
+        g->max_blocks = want;
+        g->ctx = zlb_create(env_int("ZLING_B200_DEVICE", 0, 0, 1023), want);
+        if (!g->ctx) throw std::runtime_error(std::string("libzling (B200): ") + zlb_last_error());
+        g->in_cap = (size_t) want * ZLB_BLOCK_BYTES;
+        g->out_cap = zlb_encode_bound(g->in_cap);
+        g->pin_in = (unsigned char*) zlb_host_alloc(g->in_cap + 64);
+        g->pin_out = (unsigned char*) zlb_host_alloc(g->out_cap + 64);
+        if (!g->pin_in || !g->pin_out) throw std::bad_alloc();
+        return g.release();
     }
-    return g;
-}
+    void release(Gpu* g) {
+        if (!g) return;
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            if (free_.size() < 4) { free_.push_back(g); return; }        // keep a few warm, free the rest
+        }
+        delete g;
+    }
+    ~Pool() { for (Gpu* g : free_) delete g; }
+private:
+    std::mutex m_;
+    std::vector<Gpu*> free_;
+};
+Pool& pool() { static Pool p; return p; }
+
+struct GpuLease {                        // returns the context to the pool on every exit path, exceptions included
+    Gpu* g;
+    explicit GpuLease(bool large) : g(pool().acquire(large)) {}
+    ~GpuLease() { pool().release(g); }
+    void upgrade() { Gpu* big = pool().acquire(true); pool().release(g); g = big; }
+    GpuLease(const GpuLease&) = delete;
+    GpuLease& operator=(const GpuLease&) = delete;
+};
 
 struct EncoderGuard {
     zlb_encoder* e;
@@ -126,23 +170,39 @@ bool put_all(Outputter* out, unsigned char* p, size_t len) {
 // ---- src/libzling.cpp:174-291 -------------------------------------------------------------------------------
 int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handler, int level) {
     if (level < 0 || level > 4) return -1;       // the reference never terminates here; see libzling.h
+    GpuLease lease(false);                       // acquired before OnInit: a call that cannot get a GPU throws without having started
     if (action_handler) {
         action_handler->SetInputterOutputter(inputter, outputter, true);
         action_handler->OnInit();
     }
-    Gpu& g = gpu();
-    EncoderGuard enc(zlb_encoder_begin(g.ctx, level));
+    EncoderGuard enc(zlb_encoder_begin(lease.g->ctx, level));
     if (!enc.e) raise_zlb(ZLB_E_CUDA);
 
     bool io_error = false;
+    bool upgraded = false;
+    size_t carried = 0;                          // bytes already read into the small context's staging when the input turned out longer
     while (!io_error && !inputter->IsEnd() && !inputter->IsErr()) {
         // fill up to max_blocks blocks; every block except the stream's last is exactly 16 MiB (libzling.cpp:193-196)
-        size_t have = 0;
-        while (have < g.in_cap && !inputter->IsEnd() && !inputter->IsErr()) {
-            have += inputter->GetData(g.pin_in + have, g.in_cap - have);
+        size_t have = carried;
+        carried = 0;
+        while (have < lease.g->in_cap && !inputter->IsEnd() && !inputter->IsErr()) {
+            have += inputter->GetData(lease.g->pin_in + have, lease.g->in_cap - have);
             if (inputter->IsErr()) { io_error = true; break; }
         }
         if (io_error || have == 0) break;
+        if (!upgraded && lease.g->max_blocks == 1 && have == lease.g->in_cap && !inputter->IsEnd()) {
+            upgraded = true;
+            // longer than one block: move to the large context (the encoder holds no stream state yet) and keep reading
+            std::vector<unsigned char> first(lease.g->pin_in, lease.g->pin_in + have);
+            zlb_encoder_end(enc.e); enc.e = nullptr;
+            lease.upgrade();
+            enc.e = zlb_encoder_begin(lease.g->ctx, level);
+            if (!enc.e) raise_zlb(ZLB_E_CUDA);
+            memcpy(lease.g->pin_in, first.data(), have);
+            carried = have;
+            continue;
+        }
+        Gpu& g = *lease.g;
         size_t produced = 0;
         const int rc = zlb_encode_blocks(enc.e, g.pin_in, have, g.pin_out, g.out_cap, &produced);
         if (rc != ZLB_OK) raise_zlb(rc);
@@ -168,11 +228,12 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
 
 // ---- src/libzling.cpp:293-427 -------------------------------------------------------------------------------
 int Decode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handler) {
+    GpuLease lease(action_handler == NULL);      // with a handler decode goes block by block: the small context is enough
     if (action_handler) {
         action_handler->SetInputterOutputter(inputter, outputter, false);
         action_handler->OnInit();
     }
-    Gpu& g = gpu();
+    Gpu& g = *lease.g;
     DecoderGuard dec(zlb_decoder_begin(g.ctx));
     if (!dec.d) raise_zlb(ZLB_E_CUDA);
     const int batch = action_handler ? 1 : g.max_blocks;

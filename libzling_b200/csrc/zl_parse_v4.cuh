@@ -37,17 +37,19 @@ constexpr int kV4N       = kV4W + 2;            // + two lazy look-ahead positio
 constexpr int kV4R       = 2048;                // byte ring: >= 4 + kV4N + 264 + 16
 constexpr int kV4Tail    = 288;                 // bytes staged past the last look-ahead position
 constexpr int kV4Buckets = 4096;                // buckets of the link builder
-constexpr int kV4Words   = (kV4W + 3 + 31) / 32;  // bitset words over window positions (+3: push contexts start 3 bytes early)
+constexpr int kV4Words   = (kV4W + 3 + 31) / 32 + 1;  // bitset words over window positions (+3: push contexts start 3 bytes early; +1 word: funnel reads)
 constexpr uint32_t kV4KeyInvalid = 0x80000000u; // position cannot be probed (first two bytes / last 273 bytes of the block)
 constexpr uint32_t kV4KeyMask    = 0x1fffffu;   // (context << 13) | hash slot
 constexpr uint32_t kV4Auto       = 0xffu;       // plan entry: predict the level (see v4_next_level)
 
-// decision word: len(9) | kind(3) << 9 | match idx(12) << 12
+// decision word: len(9) | kind(3) << 9 | ref(13) << 12; ref = the best candidate of a match: a ring slot of G, or
+// kV4RefWin | rel of a position of this window whose insert is still pending (its slot is known once the ranks are)
 constexpr uint32_t kV4Match = 1, kV4Lit = 2, kV4Word0 = 3, kV4Word1 = 4;
-constexpr uint32_t kV4DecCmp = 0xfffu;          // the part of a decision that defines the parse (idx is derived)
+constexpr uint32_t kV4DecCmp = 0xfffu;          // the part of a decision that defines the parse (the match idx is derived)
+constexpr uint32_t kV4RefWin = 0x1000u;
 ZL_HD uint32_t v4_dec_len(uint32_t d)  { return d & 511u; }
 ZL_HD uint32_t v4_dec_kind(uint32_t d) { return (d >> 9) & 7u; }
-ZL_HD uint32_t v4_dec_idx(uint32_t d)  { return (d >> 12) & 0xfffu; }
+ZL_HD uint32_t v4_dec_ref(uint32_t d)  { return (d >> 12) & 0x1fffu; }
 ZL_HD uint32_t v4_dec_step(uint32_t d) { const uint32_t k = v4_dec_kind(d); return k == kV4Match ? v4_dec_len(d) : (k == kV4Lit ? 1u : 2u); }
 ZL_HD uint32_t v4_dec_syms(uint32_t d) { return v4_dec_kind(d) == kV4Match ? 2u : 1u; }
 // fx word: frozen slot head (16) | flags << 16
@@ -74,6 +76,13 @@ ZL_HD int z4_clz(uint32_t v) {
     return __clz((int) v);
 #else
     return v ? __builtin_clz(v) : 32;
+#endif
+}
+ZL_HD int z4_popc(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
 #endif
 }
 ZL_HD uint64_t z4_ld_ring(const uint64_t* p) {
@@ -114,7 +123,7 @@ ZL_HD uint32_t z4_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------------
 struct V4Layout {
     int dmax, lmax;
-    int rb, key, link, blink, llen, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
+    int rb, key, link, blink, pcnt, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
     int scratch_bytes;
 };
 // scratch is a union: SPEC uses it for the link builder's bucket tables, the rounds for the orbit / rank tables
@@ -130,7 +139,7 @@ __host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
     L.key   = take(4 * kV4N);
     L.link  = take(2 * kV4N);
     L.blink = take(2 * kV4N);
-    L.llen  = take(2 * kV4N);
+    L.pcnt  = take(2 * 256);
     L.hdr   = take(4 * kV4N);
     L.node  = take(4 * kV4N * dmax);
     L.nodeq = take(4 * kV4N * lmax);
@@ -160,9 +169,11 @@ struct V4Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory (indexed by rel = x - lo unless noted)
     uint32_t* rbw;                              // input bytes: ring of kV4R bytes viewed as words, indexed by block position
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* llen; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* pcnt; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
     uint32_t* fdec; uint32_t* fx; uint16_t* rank; uint8_t* mark; uint8_t* plit; uint8_t* sup; uint32_t* dec; uint32_t* ndec;
-    uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c)
+    uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c;
+                                                // position lo + i - 2 has context c)
+    // pcnt[c] = positions of the window (incl. look-ahead) whose context byte is c: an upper bound of the inserts into c
     uint32_t* mbits;                            // [kV4Words]: bit i <=> position lo + i is a token start
     uint32_t* cnt; uint32_t* mru; uint32_t* mru2;   // carried: inserts per context before the window, word MRU at the window's entry
     uint32_t* last;                             // host replay only: bucket table of the serial link builder
@@ -170,7 +181,7 @@ struct V4Ctx {
 };
 __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.llen = (uint16_t*) (smem + L.llen); c.hdr = (uint32_t*) (smem + L.hdr);
+    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint16_t*) (smem + L.pcnt); c.hdr = (uint32_t*) (smem + L.hdr);
     c.node = (uint32_t*) (smem + L.node); c.nodeq = (uint32_t*) (smem + L.nodeq); c.fdec = (uint32_t*) (smem + L.fdec);
     c.fx = (uint32_t*) (smem + L.fx); c.rank = (uint16_t*) (smem + L.rank); c.mark = smem + L.mark; c.plit = smem + L.plit;
     c.sup = smem + L.sup; c.dec = (uint32_t*) (smem + L.dec); c.ndec = (uint32_t*) (smem + L.ndec);
@@ -253,20 +264,42 @@ ZL_HD int v4_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q) {
     const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
     return 256 + (t < 3 ? t : 3);
 }
-// the same with the candidate q read from global memory (q < x, anywhere in the block)
-ZL_HD int v4_common_len_mixed(const V4Ctx& c, uint32_t x, uint32_t q) {
-    if (v4_rb32(c.rbw, x) != z4_in32(c.in, q)) return 0;
-    for (int n = 4; n < 256; n += 4) {
-        const uint32_t d = v4_rb32(c.rbw, x + n) ^ z4_in32(c.in, q + n);
-        if (d) return n + ((z4_ffs(d) - 1) >> 3);
+// The same with the candidate q read from global memory (q < x, anywhere in the block).  The candidate's bytes come
+// in batches of aligned 16-byte loads issued together (one L2 round trip per batch instead of one per 4 bytes): 32
+// bytes first (most matches end there), then 80 at a time.
+template <int NW>     // compare NW 32-bit words at offset n; returns the number of equal leading bytes (4 * NW if all agree)
+ZL_HD int v4_cmp_words(const V4Ctx& c, uint32_t x, uint32_t q, int n) {
+    constexpr int NV = NW / 4 + 1;
+    const uint4* qa = reinterpret_cast<const uint4*>(c.in + ((q + (uint32_t) n) & ~15u));
+    uint32_t qw[4 * NV + 1];
+    #pragma unroll
+    for (int i = 0; i < NV; i++) { const uint4 v = z4_ld_in128(qa + i); qw[4 * i] = v.x; qw[4 * i + 1] = v.y; qw[4 * i + 2] = v.z; qw[4 * i + 3] = v.w; }
+    qw[4 * NV] = 0;
+    const uint32_t sh = ((q + (uint32_t) n) & 3u) * 8u, wo = ((q + (uint32_t) n) >> 2) & 3u;
+    int eq = 4 * NW;
+    #pragma unroll
+    for (int i = NW - 1; i >= 0; i--) {
+        // word i of the candidate starts at aligned word wo + i (wo = 0..3, selected without dynamic register indexing)
+        const uint32_t lo0 = wo == 0 ? qw[i] : wo == 1 ? qw[i + 1] : wo == 2 ? qw[i + 2] : qw[i + 3];
+        const uint32_t hi0 = wo == 0 ? qw[i + 1] : wo == 1 ? qw[i + 2] : wo == 2 ? qw[i + 3] : qw[i + 4];
+        const uint32_t d = z4_funnel(lo0, hi0, sh) ^ v4_rb32(c.rbw, x + (uint32_t) n + 4u * (uint32_t) i);
+        if (d) eq = 4 * i + ((z4_ffs(d) - 1) >> 3);
     }
-    const uint32_t d = v4_rb32(c.rbw, x + 256) ^ z4_in32(c.in, q + 256);
-    const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
-    return 256 + (t < 3 ? t : 3);
+    return eq;
+}
+ZL_HD int v4_common_len_mixed(const V4Ctx& c, uint32_t x, uint32_t q) {
+    int e = v4_cmp_words<8>(c, x, q, 0);
+    if (e < 4) return 0;
+    if (e < 32) return e;
+    for (int n = 32; n < 240; n += 80) {
+        e = v4_cmp_words<20>(c, x, q, n);
+        if (e < 80) { const int l = n + e; return l < kMaxLen ? l : kMaxLen; }
+    }
+    return kMaxLen;                                                      // 272 bytes agree; the length is capped at 259
 }
 
-// ---- SPEC C: nearest earlier position of the window with the same key, and the match length against it ---------------------
-ZL_HD void v4_link_position(const V4Ctx& c, int lo, int rel) {
+// ---- SPEC C: nearest earlier position of the window with the same key -----------------------------------------------------
+ZL_HD void v4_link_position(const V4Ctx& c, int rel) {
     const uint32_t k = c.key[rel];
     uint32_t out = 0;
     if (!(k & kV4KeyInvalid)) {
@@ -279,7 +312,6 @@ ZL_HD void v4_link_position(const V4Ctx& c, int lo, int rel) {
         }
     }
     c.link[rel] = (uint16_t) out;
-    c.llen[rel] = out ? (uint16_t) v4_common_len_ring(c.rbw, (uint32_t) (lo + rel), (uint32_t) (lo + rel) - out) : (uint16_t) 0;
 }
 
 // ---- SPEC D: chain record of a position against the frozen bucket state G -----------------------------------------------
@@ -364,16 +396,31 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
 // While position x (rel) is being decided the reference's bucket state is G plus the inserts of the marked positions
 // before x plus x's own insert (the insert precedes the search, lz.cpp:227-230).
 ZL_HD bool v4_pending(const V4Ctx& c, int xrel, int y) { return y == xrel || (y < xrel && c.mark[y] != 0); }
-ZL_HD uint32_t v4_head_of(const V4Ctx& c, int rel) {                    // ring slot of the insert made at rel
+// window positions [32 w, 32 w + 32) whose context byte is cq (position rel has context cq <=> bit rel + 2 of occ[cq])
+ZL_HD uint32_t v4_ctxbits(const V4Ctx& c, uint32_t cq, int w) {
+    const uint32_t* o = c.occ + cq * kV4Words;
+    return z4_funnel(o[w], o[w + 1], 2);
+}
+// inserts into context cq pending before rel: marked positions y < rel with that context.  Exact, on demand (the
+// per-context ranks of ALL positions are only built once per window, after the rounds: v4_head_final)
+ZL_HD uint32_t v4_rank_live(const V4Ctx& c, int rel, uint32_t cq) {
+    uint32_t n = 0;
+    const int wl = rel >> 5;
+    for (int w = 0; w < wl; w++) n += (uint32_t) z4_popc(v4_ctxbits(c, cq, w) & c.mbits[w]);
+    if (rel & 31) n += (uint32_t) z4_popc(v4_ctxbits(c, cq, wl) & c.mbits[wl] & ((1u << (rel & 31)) - 1u));
+    return n;
+}
+ZL_HD uint32_t v4_head_live(const V4Ctx& c, int rel) {                  // ring slot of the insert made at rel, from the marks
+    const uint32_t cq = v4_ctx_of(c.key[rel]);
+    return (c.cnt[cq] + v4_rank_live(c, rel, cq) + 1u) & (kRing - 1);
+}
+ZL_HD uint32_t v4_head_final(const V4Ctx& c, int rel) {                 // the same from the rank table (FINALIZE)
     return (c.cnt[v4_ctx_of(c.key[rel])] + c.rank[rel] + 1u) & (kRing - 1);
 }
 // inserts into the context of position rel + q (q = 1, 2) made before and at rel
 ZL_HD uint32_t v4_cnt_lazy(const V4Ctx& c, int rel, int q) {
     const uint32_t cw = v4_ctx_of(c.key[rel + q]);
-    uint32_t n = c.rank[rel + q];
-    for (int i = rel; i < rel + q; i++) if (c.mark[i] && v4_ctx_of(c.key[i]) == cw) n--;
-    if (v4_ctx_of(c.key[rel]) == cw) n++;
-    return n;
+    return v4_rank_live(c, rel, cw) + (v4_ctx_of(c.key[rel]) == cw ? 1u : 0u);
 }
 // is some same-key position before z, not after xrel, pending?
 ZL_HD bool v4_link_hazard(const V4Ctx& c, int z, int xrel, bool self_counts) {
@@ -396,29 +443,42 @@ ZL_HD int v4_valid_nodes(const V4Ctx& c, int rel, int nvis, uint32_t head_b, uin
     while (i < nvis && v4_ring_dist(c.node[rel * c.dmax + i] >> 9, head_b) > kc) i++;
     return i;
 }
+// Could a slot read by the record of rel have been overwritten by this window's inserts?  (static bound: pcnt)
+ZL_HD bool v4_maybe_stale(const V4Ctx& c, int rel, uint32_t hdr, uint32_t extra) {
+    return (hdr & 31u) && (hdr >> 5) + 1u <= (uint32_t) c.pcnt[v4_ctx_of(c.key[rel])] + extra;
+}
 // slot head seen by the insert at y: the nearest marked same-key position before it, else the frozen head
-ZL_HD uint32_t v4_suffix_of(const V4Ctx& c, int y) {
+ZL_HD uint32_t v4_suffix_live(const V4Ctx& c, int y) {
     int t = y;
     while (true) {
         const uint32_t d = c.link[t];
         if (!d) break;
         t -= (int) d;
-        if (c.mark[t]) return v4_head_of(c, t);
+        if (c.mark[t]) return v4_head_live(c, t);
     }
     return c.fx[y] & 0xffffu;
 }
-// the reference's ring[ctx][n] as seen while xrel is decided
-ZL_HD uint64_t v4_live_entry(const V4Ctx& c, int lo, int xrel, uint32_t ctx, uint32_t n) {
-    const uint32_t ord = (n - c.cnt[ctx]) & (kRing - 1);
+// the reference's ring[cq][n] as seen while xrel is decided
+ZL_HD uint64_t v4_live_entry(const V4Ctx& c, int lo, int xrel, uint32_t cq, uint32_t n) {
+    const uint32_t ord = (n - c.cnt[cq]) & (kRing - 1);                  // n is pending iff it is insert number 1.. of this window
     if (ord != 0 && ord <= (uint32_t) kV4N) {
-        for (int y = xrel; y >= 0; y--) {
-            if (!v4_pending(c, xrel, y)) continue;
-            const uint32_t k = c.key[y];
-            if ((k & kV4KeyInvalid) || v4_ctx_of(k) != ctx) continue;
-            if (v4_head_of(c, y) == n) return ring_make((uint32_t) (lo + y), k >> 21, v4_suffix_of(c, y));
+        // the ord-th position with context cq among the pending ones (marked before xrel; xrel itself comes last)
+        uint32_t left = ord;
+        const int wl = xrel >> 5;
+        for (int w = 0; w <= wl; w++) {
+            uint32_t m = v4_ctxbits(c, cq, w) & c.mbits[w];
+            if (w == wl) m &= (1u << (xrel & 31)) - 1u;
+            const uint32_t pc = (uint32_t) z4_popc(m);
+            if (left <= pc) {
+                for (uint32_t i = 1; i < left; i++) m &= m - 1u;         // drop the left-1 lowest set bits
+                const int y = w * 32 + z4_ffs(m) - 1;
+                return ring_make((uint32_t) (lo + y), c.key[y] >> 21, v4_suffix_live(c, y));
+            }
+            left -= pc;
         }
+        if (left == 1 && v4_ctx_of(c.key[xrel]) == cq) return ring_make((uint32_t) (lo + xrel), c.key[xrel] >> 21, v4_suffix_live(c, xrel));
     }
-    return z4_ld_ring(c.ring + (size_t) ctx * kRing + n);
+    return z4_ld_ring(c.ring + (size_t) cq * kRing + n);
 }
 ZL_HD int v4_common_len_any(const V4Ctx& c, uint32_t x, uint32_t q) {     // both operands from global memory
     if (z4_in32(c.in, x) != z4_in32(c.in, q)) return 0;
@@ -431,10 +491,10 @@ ZL_HD int v4_common_len_any(const V4Ctx& c, uint32_t x, uint32_t q) {     // bot
     return 256 + (t < 3 ? t : 3);
 }
 // literal replay of the candidate walk of MatchAndUpdate (lz.cpp:234-267) on the pending view
-ZL_HD int v4_main_live(const V4Ctx& c, int lo, int xrel, uint32_t node, uint32_t head, uint32_t chk, uint32_t ctx, int D, uint32_t* bestslot) {
+ZL_HD int v4_main_live(const V4Ctx& c, int lo, int xrel, uint32_t node, uint32_t head, uint32_t chk, uint32_t cq, int D, uint32_t* bestslot) {
     if (node == (uint32_t) kNil || node == head) return 0;
     int best = kMinLen - 1;
-    uint64_t e = v4_live_entry(c, lo, xrel, ctx, node);
+    uint64_t e = v4_live_entry(c, lo, xrel, cq, node);
     for (int hop = 0; hop < D; hop++) {
         const uint32_t cand = ring_pos(e);
         if (ring_check(e) == chk) {
@@ -443,7 +503,7 @@ ZL_HD int v4_main_live(const V4Ctx& c, int lo, int xrel, uint32_t node, uint32_t
         }
         const uint32_t nxt = ring_suffix(e);
         if (nxt == (uint32_t) kNil) break;
-        const uint64_t e2 = v4_live_entry(c, lo, xrel, ctx, nxt);
+        const uint64_t e2 = v4_live_entry(c, lo, xrel, cq, nxt);
         if (cand <= ring_pos(e2)) break;
         node = nxt; e = e2;
     }
@@ -452,27 +512,27 @@ ZL_HD int v4_main_live(const V4Ctx& c, int lo, int xrel, uint32_t node, uint32_t
 // literal replay of MatchLazy (lz.cpp:291-316) at position zrel on the pending view of xrel
 ZL_HD bool v4_lazy_live(const V4Ctx& c, int lo, int xrel, int zrel, int best, int depth) {
     const uint32_t k = c.key[zrel];
-    const uint32_t ctx = v4_ctx_of(k);
-    uint32_t node = c.fx[zrel] & 0xffffu;                                // hash[ctx][slot]: newest pending same-key insert, else G's
+    const uint32_t cq = v4_ctx_of(k);
+    uint32_t node = c.fx[zrel] & 0xffffu;                                // hash[cq][slot]: newest pending same-key insert, else G's
     {
         int y = zrel;
         while (true) {
             const uint32_t d = c.link[y];
             if (!d) break;
             y -= (int) d;
-            if (y <= xrel && v4_pending(c, xrel, y)) { node = v4_head_of(c, y); break; }
+            if (y <= xrel && v4_pending(c, xrel, y)) { node = v4_head_live(c, y); break; }
         }
     }
     if (node == (uint32_t) kNil) return false;
     const uint32_t at = (uint32_t) best - 3u;
     const uint32_t mine = z4_in32(c.in, (uint32_t) (lo + zrel) + at);
-    uint64_t e = v4_live_entry(c, lo, xrel, ctx, node);
+    uint64_t e = v4_live_entry(c, lo, xrel, cq, node);
     for (int hop = 0; hop < depth; hop++) {
         const uint32_t cand = ring_pos(e);
         if (z4_in32(c.in, cand + at) == mine) return true;
         const uint32_t nxt = ring_suffix(e);
         if (nxt == (uint32_t) kNil) break;
-        const uint64_t e2 = v4_live_entry(c, lo, xrel, ctx, nxt);
+        const uint64_t e2 = v4_live_entry(c, lo, xrel, cq, nxt);
         if (cand <= ring_pos(e2)) break;
         e = e2;
     }
@@ -480,18 +540,21 @@ ZL_HD bool v4_lazy_live(const V4Ctx& c, int lo, int xrel, int zrel, int best, in
 }
 
 // Does the frozen decision at rel NOT stand because of the inserts pending in the window?
-ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, uint32_t kc0, int L2) {
+ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, int L2) {
     const uint32_t fbest = (fd >> 9) & 511u;
     const int nlazy = (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) ? (L2 > 0 ? 2 : 1) : 0;
     if ((fxw & kV4F_SELF) && v4_link_hazard(c, rel, rel, false)) return true;
     if (nlazy >= 1 && (fxw & kV4F_L1) && v4_link_hazard(c, rel + 1, rel, true)) return true;
     if (nlazy >= 2 && (fxw & kV4F_L2) && v4_link_hazard(c, rel + 2, rel, true)) return true;
-    const uint32_t ctx = v4_ctx_of(c.key[rel]);
     const uint32_t h0 = c.hdr[rel];
-    if ((h0 & 31u) && (h0 >> 5) + 1u <= kc0 && v4_valid_nodes(c, rel, (int) (h0 & 31u), c.cnt[ctx] & (kRing - 1), kc0) < (int) (h0 & 31u)) return true;
+    if (v4_maybe_stale(c, rel, h0, 0)) {
+        const uint32_t cq = v4_ctx_of(c.key[rel]);
+        const uint32_t kc0 = v4_rank_live(c, rel, cq) + 1u;
+        if ((h0 >> 5) + 1u <= kc0 && v4_valid_nodes(c, rel, (int) (h0 & 31u), c.cnt[cq] & (kRing - 1), kc0) < (int) (h0 & 31u)) return true;
+    }
     for (int q = 1; q <= nlazy; q++) {
         const uint32_t hw = c.hdr[rel + q];
-        if (!(hw & 31u)) continue;
+        if (!v4_maybe_stale(c, rel + q, hw, 1)) continue;
         const uint32_t cw = v4_ctx_of(c.key[rel + q]);
         const uint32_t kc = v4_cnt_lazy(c, rel, q);
         if ((hw >> 5) + 1u <= kc && v4_valid_nodes(c, rel + q, (int) (hw & 31u), c.cnt[cw] & (kRing - 1), kc) < (int) (hw & 31u)) return true;
@@ -500,15 +563,16 @@ ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, uint32_
 }
 
 // The full MatchAndUpdate (lz.cpp:211-289) at rel on the pending view: in-window candidates (newest first), then the
-// frozen record.  Returns the match length (0 = none) and the ring slot of the best candidate.
-ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t kc0, uint32_t head, uint32_t* bestslot_out) {
+// frozen record.  Returns the match length (0 = none) and the reference to the best candidate (a ring slot, or
+// kV4RefWin | rel of a pending position).
+ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t* ref_out) {
     const int x = lo + rel;
     const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
     const uint32_t kx = c.key[rel];
-    const uint32_t chk = kx >> 21, ctx = v4_ctx_of(kx);
-    int best = kMinLen - 1, visited = 0;
-    uint32_t bestslot = 0, suffix = c.fx[rel] & 0xffffu;
-    bool done = false, have_suffix = false;
+    const uint32_t chk = kx >> 21, cq = v4_ctx_of(kx);
+    int best = kMinLen - 1, visited = 0, first_pending = -1;
+    uint32_t ref = 0;
+    bool done = false;
     {
         int y = rel;
         while (true) {
@@ -516,12 +580,12 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t 
             if (!dl) break;
             y -= (int) dl;
             if (!c.mark[y]) continue;
-            if (!have_suffix) { suffix = v4_head_of(c, y); have_suffix = true; }
+            if (first_pending < 0) first_pending = y;
             if (visited < D && !done) {
                 visited++;
                 if ((c.key[y] >> 21) == chk) {
-                    const int l = y == rel - (int) c.link[rel] ? (int) c.llen[rel] : v4_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) (lo + y));
-                    if (l > best) { best = l; bestslot = v4_head_of(c, y); if (best == kMaxLen) done = true; }
+                    const int l = v4_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) (lo + y));
+                    if (l > best) { best = l; ref = kV4RefWin | (uint32_t) y; if (best == kMaxLen) done = true; }
                 }
             } else break;
         }
@@ -529,22 +593,28 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t 
     const uint32_t hdr = c.hdr[rel];
     int nvis = (int) (hdr & 31u);
     bool stale0 = false;
-    if (nvis > 0 && (hdr >> 5) + 1u <= kc0) {
-        const int nv = v4_valid_nodes(c, rel, nvis, c.cnt[ctx] & (kRing - 1), kc0);
-        stale0 = nv == 0;
-        nvis = nv;
+    uint32_t kc0 = 0;
+    if (v4_maybe_stale(c, rel, hdr, 0)) {
+        kc0 = v4_rank_live(c, rel, cq) + 1u;
+        if ((hdr >> 5) + 1u <= kc0) {
+            const int nv = v4_valid_nodes(c, rel, nvis, c.cnt[cq] & (kRing - 1), kc0);
+            stale0 = nv == 0;
+            nvis = nv;
+        }
     }
     if (!done && visited < D && (nvis > 0 || stale0)) {
         if (stale0) {                                                    // the record's first slot has been overwritten: replay literally
+            const uint32_t head = (c.cnt[cq] + kc0) & (kRing - 1);
+            const uint32_t suffix = first_pending >= 0 ? v4_head_live(c, first_pending) : (c.fx[rel] & 0xffffu);
             uint32_t bn = 0;
-            best = v4_main_live(c, lo, rel, suffix, head, chk, ctx, D, &bn);
-            bestslot = bn;
+            best = v4_main_live(c, lo, rel, suffix, head, chk, cq, D, &bn);
+            ref = bn;
         } else {
             const int take = nvis < D - visited ? nvis : D - visited;
             for (int i = 0; i < take; i++) {
                 const uint32_t nd = c.node[rel * c.dmax + i];
                 const int l = (int) (nd & 511u);
-                if (l > best) { best = l; bestslot = nd >> 9; if (best == kMaxLen) break; }
+                if (l > best) { best = l; ref = nd >> 9; if (best == kMaxLen) break; }
             }
         }
     }
@@ -555,15 +625,17 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t 
             const int depth = which == 1 ? L1 : L2;
             if (depth == 0) break;
             const int relz = rel + which;
-            const uint32_t cz = v4_ctx_of(c.key[relz]);
             const uint32_t hz = c.hdr[relz];
             int nvz = (int) (hz & 31u);
-            const uint32_t kcz = v4_cnt_lazy(c, rel, which);
-            if (nvz > 0 && (hz >> 5) + 1u <= kcz) {                      // stale lazy record: cut it, or replay when its head is gone
-                nvz = v4_valid_nodes(c, relz, nvz, c.cnt[cz] & (kRing - 1), kcz);
-                if (nvz == 0) {
-                    if (v4_lazy_live(c, lo, rel, relz, best, depth)) return 0;
-                    continue;
+            if (v4_maybe_stale(c, relz, hz, 1)) {                        // stale lazy record: cut it, or replay when its head is gone
+                const uint32_t cz = v4_ctx_of(c.key[relz]);
+                const uint32_t kcz = v4_cnt_lazy(c, rel, which);
+                if ((hz >> 5) + 1u <= kcz) {
+                    nvz = v4_valid_nodes(c, relz, nvz, c.cnt[cz] & (kRing - 1), kcz);
+                    if (nvz == 0) {
+                        if (v4_lazy_live(c, lo, rel, relz, best, depth)) return 0;
+                        continue;
+                    }
                 }
             }
             const uint32_t mine = v4_rb32(c.rbw, (uint32_t) (lo + relz) + at);
@@ -583,7 +655,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t 
                 if (z4_in32(c.in, c.nodeq[relz * c.lmax + i] + at) == mine) return 0;
         }
     }
-    *bestslot_out = bestslot;
+    *ref_out = ref;
     return best;
 }
 
@@ -632,23 +704,20 @@ ZL_HD uint32_t v4_decide(const V4Ctx& c, const V4Win& w, int rel) {
     const int x = w.lo + rel;
     const int level = (w.rpos >= 0 && x >= w.rpos) ? w.level2 : w.level;
     const uint32_t fd = c.fdec[rel], fxw = c.fx[rel];
-    const uint32_t kx = c.key[rel], ctx = v4_ctx_of(kx);
-    const uint32_t kc0 = (uint32_t) c.rank[rel] + 1u;
-    const uint32_t head = (c.cnt[ctx] + kc0) & (kRing - 1);
-    uint32_t len = fd & 511u, bestslot = (fd >> 18) & (kRing - 1);
-    if (level != w.level || v4_hazard(c, rel, fd, fxw, kc0, depth_lazy2(level))) {
-        uint32_t bs = 0;
-        len = (uint32_t) v4_probe_general(c, w.lo, rel, level, kc0, head, &bs);
-        bestslot = bs;
+    uint32_t len = fd & 511u, ref = (fd >> 18) & (kRing - 1);
+    if (level != w.level || v4_hazard(c, rel, fd, fxw, depth_lazy2(level))) {
+        uint32_t rf = 0;
+        len = (uint32_t) v4_probe_general(c, w.lo, rel, level, &rf);
+        ref = rf;
     }
-    if (len) return len | (kV4Match << 9) | (((head - bestslot) & (kRing - 1)) << 12);
-    const uint32_t m = v4_mru_state(c, w, rel, ctx);                    // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
+    if (len) return len | (kV4Match << 9) | (ref << 12);
+    const uint32_t m = v4_mru_state(c, w, rel, v4_ctx_of(c.key[rel]));  // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
     const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
     const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
     return kind << 9;
 }
 
-// ---- FINALIZE ---------------------------------------------------------------------------------------------------------------
+// ---- FINALIZE (the rank table is valid now) ------------------------------------------------------------------------------------
 // marked position rel: find the slot head its insert replaces, and tell the previous owner of the slot that it has been superseded
 ZL_HD uint32_t v4_claim_slot(const V4Ctx& c, int rel) {
     int t = rel;
@@ -656,22 +725,24 @@ ZL_HD uint32_t v4_claim_slot(const V4Ctx& c, int rel) {
         const uint32_t d = c.link[t];
         if (!d) break;
         t -= (int) d;
-        if (c.mark[t]) { c.sup[t] = 1; return v4_head_of(c, t); }
+        if (c.mark[t]) { c.sup[t] = 1; return v4_head_final(c, t); }
     }
     return c.fx[rel] & 0xffffu;
 }
 ZL_HD void v4_apply_position(const V4Ctx& c, int lo, int rel, uint32_t suffix) {
     const uint32_t k = c.key[rel];
-    const uint32_t ctx = v4_ctx_of(k), slot = k & (kSlots - 1), chk = k >> 21, head = v4_head_of(c, rel);
-    c.ring[(size_t) ctx * kRing + head] = ring_make((uint32_t) (lo + rel), chk, suffix);
-    if (!c.sup[rel]) c.hash[(size_t) ctx * kSlots + slot] = (uint16_t) head;
+    const uint32_t cq = v4_ctx_of(k), slot = k & (kSlots - 1), chk = k >> 21, head = v4_head_final(c, rel);
+    c.ring[(size_t) cq * kRing + head] = ring_make((uint32_t) (lo + rel), chk, suffix);
+    if (!c.sup[rel]) c.hash[(size_t) cq * kSlots + slot] = (uint16_t) head;
 }
 ZL_HD uint32_t v4_token_of(const V4Ctx& c, int lo, int rel) {
     const uint32_t d = c.dec[rel], kind = v4_dec_kind(d);
     if (kind == kV4Lit) return tok_literal(v4_rb8(c.rbw, (uint32_t) (lo + rel)), v4_rb8(c.rbw, (uint32_t) (lo + rel) - 1), false);
     if (kind == kV4Word0) return tok_word(0);
     if (kind == kV4Word1) return tok_word(1);
-    return tok_match(v4_dec_len(d), v4_dec_idx(d));
+    const uint32_t ref = v4_dec_ref(d);
+    const uint32_t slot = (ref & kV4RefWin) ? v4_head_final(c, (int) (ref & (kV4RefWin - 1))) : ref;
+    return tok_match(v4_dec_len(d), (v4_head_final(c, rel) - slot) & (kRing - 1));     // lz.cpp:283
 }
 
 // ---- resolver state carried across windows ------------------------------------------------------------------------------------
@@ -743,6 +814,15 @@ namespace zl {
 struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide; };
 
 __device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
+// warp 0: per-warp totals arr[0..31] -> exclusive prefix in place, grand total in arr[32] (callers synchronise around it)
+__device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
+    const int v = arr[lane];
+    int incl = v;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    arr[lane] = incl - v;
+    if (lane == 31) arr[32] = incl;
+}
 
 // ---- the kernel: grid = blocks of the batch, kV4W threads, thread t owns position lo + t of the current window -----------
 __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int dmax, int lmax, int base_level, V4Counters* counters) {
@@ -751,8 +831,8 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ V4Run s_run;
     __shared__ V4Win s_win;
-    __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos, s_syms, s_syms_after;
-    __shared__ int s_wtok[kV4W / 32], s_wlit[kV4W / 32], s_wsym[kV4W / 32];
+    __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
+    __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
     const V4Layout L = v4_layout(dmax, lmax);
     V4Ctx c;
     v4_bind(c, smem_raw, L);
@@ -763,9 +843,8 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     const int ilen = c.ilen;
     uint8_t* scratch = smem_raw + L.scratch;
     uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
-    constexpr int kJStride = (kV4N * 2 + 15) & ~15;
-    uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + kV4Levels * kJStride);   // ROUNDS: [33][256] marked positions per (warp, context)
-    auto J = [&](int l) { return reinterpret_cast<uint16_t*>(scratch + l * kJStride); };
+    uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
+    uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + 4096);                   // FINALIZE: [33][256] marked positions per (warp, context)
 
     for (int i = tid; i < 256; i += kV4W) { c.cnt[i] = 0; c.mru[i] = 0; }
     long long cyc_spec = 0, cyc_rounds = 0, cyc_final = 0, cyc_orbit = 0, cyc_rank = 0, cyc_decide = 0;
@@ -785,6 +864,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     const int lim = ilen - kGuard;
     const int nwin = lim > 2 ? (lim + kV4W - 1) / kV4W : 0;              // windows that contain probe positions
     int staged_hi = -16;
+    const int segbase = warp * 32, segend = segbase + 32;
 
     for (int k = 0; k < nwin; k++) {
         const int lo = k * kV4W;
@@ -802,12 +882,12 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         for (int i = tid; i < 256 * kV4Words; i += kV4W) c.occ[i] = 0;
         { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4W) z[i] = make_uint4(0, 0, 0, 0); }
         __syncthreads();
-        {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..2 also bits W..W+2
+        {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..3 also bits W..W+3
             const int p = lo + tid - 3;
             const uint32_t v = p >= 0 ? v4_rb8(c.rbw, (uint32_t) p) : 256u + (uint32_t) lane;
             const uint32_t grp = __match_any_sync(0xffffffffu, v);
             if (p >= 0 && (grp >> lane) == 1u) c.occ[v * kV4Words + warp] = grp;
-            if (tid < 3) { const int p2 = lo + kV4W + tid - 3; atomicOr(&c.occ[v4_rb8(c.rbw, (uint32_t) p2) * kV4Words + (kV4W >> 5)], 1u << tid); }
+            if (tid < 4) { const int p2 = lo + kV4W + tid - 3; atomicOr(&c.occ[v4_rb8(c.rbw, (uint32_t) p2) * kV4Words + (kV4W >> 5)], 1u << tid); }
         }
         v4_spec_position(c, lo, tid);                                    // chain records against G (global-memory latency lives here)
         if (tid < 2) v4_spec_position(c, lo, kV4W + tid);
@@ -856,10 +936,15 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                     c.blink[rel] = (uint16_t) d2;
                 }
             }
+            if (tid >= 256 && tid < 512) {                               // pcnt[ctx]: window positions with that context byte
+                uint32_t n = 0;
+                for (int wq = 0; wq < kV4Words - 1; wq++) n += (uint32_t) __popc(v4_ctxbits(c, (uint32_t) (tid - 256), wq));
+                c.pcnt[tid - 256] = (uint16_t) n;
+            }
         }
         __syncthreads();
-        v4_link_position(c, lo, tid);
-        if (tid < 2) v4_link_position(c, lo, kV4W + tid);
+        v4_link_position(c, tid);
+        if (tid < 2) v4_link_position(c, kV4W + tid);
         __syncthreads();
         const int wlevel = s_run.level;
         v4_frozen_position(c, lo, tid, wlevel);
@@ -870,58 +955,47 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         }
         { const uint32_t fl = c.fdec[tid] & 511u; c.dec[tid] = fl ? (fl | (kV4Match << 9)) : (kV4Lit << 9); }
         if (tid < 2) { c.dec[kV4W + tid] = kV4Lit << 9; c.mark[kV4W + tid] = 0; c.plit[kV4W + tid] = 0; }
-        if (tid == 0) c.mbits[kV4W >> 5] = 0;
+        if (tid < 2) c.mbits[(kV4W >> 5) + tid] = 0;
         __syncthreads();
         const long long t1 = clock64();
         cyc_spec += t1 - t0;
         // ================================================= ROUNDS ===============================================
         const int entry_rel = s_win.entry - lo;
         const bool may_roll = s_run.op + 2 * kV4N + 1 >= kSubSymbols;
+        bool marked = false;
         while (true) {
             n_rounds++;
             const long long r0 = clock64();
-            // ---- orbit of the entry under next = x + step(decision): pointer doubling
+            // ---- orbit of the entry under next = x + step(decision).  Inside a 32-position segment: pointer doubling with
+            // shuffles; across segments: every warp chases the segment exits from the window's entry up to its own segment
             const uint32_t mydec = c.dec[tid];
-            { uint32_t t = tid < Wn ? (uint32_t) tid + v4_dec_step(mydec) : (uint32_t) Wn; if (t > (uint32_t) Wn) t = (uint32_t) Wn;
-              J(0)[tid] = (uint16_t) t; if (tid < 2) J(0)[kV4W + tid] = (uint16_t) Wn; }
-            c.mark[tid] = tid == entry_rel;
+            int cj[6];
+            { int t = tid < Wn ? tid + (int) v4_dec_step(mydec) : Wn; cj[0] = t < Wn ? t : Wn; }
+            #pragma unroll
+            for (int l = 0; l < 5; l++) { const int nx = __shfl_sync(0xffffffffu, cj[l], cj[l] & 31); cj[l + 1] = cj[l] < segend ? nx : cj[l]; }
+            E[tid] = (uint16_t) cj[5];
             c.plit[tid] = 0;
+            if (tid == 0) s_rpos_rel = 0x7fffffff;
             __syncthreads();
-            int nlev = 1;
-            for (; nlev < kV4Levels - 1; nlev++) {
-                if (J(nlev - 1)[entry_rel] >= Wn) break;                 // 2^(nlev-1) steps leave the window: enough levels
-                const uint16_t* jp = J(nlev - 1);
-                J(nlev)[tid] = jp[jp[tid]];
-                if (tid < 2) J(nlev)[kV4W + tid] = (uint16_t) Wn;
-                __syncthreads();
+            int cur = entry_rel;
+            while ((cur >> 5) < warp && cur < Wn) cur = E[cur];
+            uint32_t M = ((cur >> 5) == warp && cur < Wn) ? 1u << (cur & 31) : 0u;
+            #pragma unroll
+            for (int l = 4; l >= 0; l--) {
+                const int tg = cj[l];
+                const uint32_t contrib = (((M >> lane) & 1u) && tg < segend && tg < Wn) ? 1u << (tg & 31) : 0u;
+                M |= __reduce_or_sync(0xffffffffu, contrib);
             }
-            for (int l = nlev - 1; l >= 0; l--) {
-                if (c.mark[tid]) { const int t = J(l)[tid]; if (t < Wn) c.mark[t] = 1; }
-                __syncthreads();
-            }
-            const bool marked = c.mark[tid] != 0;
+            marked = (M >> lane) & 1u;
+            c.mark[tid] = (uint8_t) marked;
+            if (lane == 0) c.mbits[warp] = M;
             if (marked) {
-                const int t = (int) tid + (int) v4_dec_step(mydec);
+                const int t = tid + (int) v4_dec_step(mydec);
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
                 else { s_exit = lo + t; s_lastrel = tid; }
             }
-            { const uint32_t mb = __ballot_sync(0xffffffffu, marked); if (lane == 0) c.mbits[warp] = mb; }
-            // ---- per-context ranks of the marked positions
-            reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
-            if (tid == 0) { s_rpos_rel = 0x7fffffff; }
-            __syncthreads();
             const long long r1 = clock64();
-            const uint32_t kx = c.key[tid];
-            const bool valid = !(kx & kV4KeyInvalid);
-            const uint32_t ctx = v4_ctx_of(kx);
-            uint32_t inwarp = 0;
-            {
-                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? ctx : 256u + (uint32_t) lane);
-                const uint32_t mk = __ballot_sync(0xffffffffu, marked);
-                inwarp = (uint32_t) __popc(grp & mk & v4_lt_mask(lane));
-                if (valid && (grp >> lane) == 1u) wcnt[warp * 256 + ctx] = (uint16_t) __popc(grp & mk);
-            }
-            // sub-block roll-over (rare): symbols before each marked position
+            // ---- sub-block roll-over (rare): symbols before each marked position
             if (may_roll) {
                 const uint32_t mysym = marked ? v4_dec_syms(mydec) : 0u;
                 uint32_t incl = mysym;
@@ -929,32 +1003,23 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
                 if (lane == 31) s_wsym[warp] = (int) incl;
                 __syncthreads();
-                int before = s_run.op;
-                for (int w2 = 0; w2 < warp; w2++) before += s_wsym[w2];
-                before += (int) (incl - mysym);
+                if (warp == 0) v4_warp0_prefix(s_wsym, lane);
+                __syncthreads();
+                const int before = s_run.op + s_wsym[warp] + (int) (incl - mysym);
                 if (marked && before + 1 >= kSubSymbols) atomicMin(&s_rpos_rel, tid);
                 __syncthreads();
                 if (s_rpos_rel == tid) s_op_at_rpos = before;
-            }
-            __syncthreads();
-            if (tid < 256) {
-                uint32_t run = 0;
-                #pragma unroll 8
-                for (int w2 = 0; w2 < 32; w2++) { const uint32_t t = wcnt[w2 * 256 + tid]; wcnt[w2 * 256 + tid] = (uint16_t) run; run += t; }
-                wcnt[32 * 256 + tid] = (uint16_t) run;
-            }
-            if (tid == 0) {
-                V4Win w = s_win;
-                w.rpos = -1; w.level2 = w.level;
-                if (may_roll && s_rpos_rel != 0x7fffffff) {
-                    w.rpos = lo + s_rpos_rel;
-                    w.level2 = v4_next_level(c, s_run.j + 1, w.rpos - s_run.enc_begin, s_op_at_rpos);
+                __syncthreads();
+                if (tid == 0) {
+                    V4Win w = s_win;
+                    w.rpos = -1; w.level2 = w.level;
+                    if (s_rpos_rel != 0x7fffffff) {
+                        w.rpos = lo + s_rpos_rel;
+                        w.level2 = v4_next_level(c, s_run.j + 1, w.rpos - s_run.enc_begin, s_op_at_rpos);
+                    }
+                    s_win = w;
                 }
-                s_win = w;
             }
-            __syncthreads();
-            c.rank[tid] = valid ? (uint16_t) (wcnt[warp * 256 + ctx] + inwarp) : (uint16_t) 0;
-            if (tid < 2) { const uint32_t k2 = c.key[kV4W + tid]; c.rank[kV4W + tid] = (k2 & kV4KeyInvalid) ? (uint16_t) 0 : wcnt[32 * 256 + v4_ctx_of(k2)]; }
             __syncthreads();
             const long long r2 = clock64();
             // ---- every position re-derives its decision
@@ -966,23 +1031,28 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             const long long r3 = clock64();
             cyc_orbit += r1 - r0; cyc_rank += r2 - r1; cyc_decide += r3 - r2;
             if (!changed) break;
-            __syncthreads();
         }
-        __syncthreads();
         const long long t2 = clock64();
         cyc_rounds += t2 - t1;
         n_windows++;
         // ================================================= FINALIZE =============================================
         {
             const V4Win w = s_win;
-            const bool marked = c.mark[tid] != 0;
             const uint32_t d = c.dec[tid];
+            // per-context ranks of the marked positions -> ring slots of the pending inserts
+            reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
             c.sup[tid] = 0;
             __syncthreads();
-            uint32_t suffix = 0;
-            if (marked) suffix = v4_claim_slot(c, tid);
-            __syncthreads();
-            if (marked) v4_apply_position(c, lo, tid, suffix);
+            const uint32_t kx = c.key[tid];
+            const bool valid = !(kx & kV4KeyInvalid);
+            const uint32_t ctx = v4_ctx_of(kx);
+            uint32_t inwarp = 0;
+            {
+                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? ctx : 256u + (uint32_t) lane);
+                const uint32_t mk = __ballot_sync(0xffffffffu, marked);
+                inwarp = (uint32_t) __popc(grp & mk & v4_lt_mask(lane));
+                if (valid && (grp >> lane) == 1u) wcnt[warp * 256 + ctx] = (uint16_t) __popc(grp & mk);
+            }
             const bool islit = marked && v4_dec_kind(d) == kV4Lit;
             const uint32_t bt = __ballot_sync(0xffffffffu, marked), bl = __ballot_sync(0xffffffffu, islit);
             const bool after = w.rpos >= 0 && lo + tid >= w.rpos;
@@ -990,34 +1060,43 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             uint32_t sya = after ? sy : 0u;
             #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, o); sya += __shfl_xor_sync(0xffffffffu, sya, o); }
-            if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); s_wsym[warp] = (int) (sy | (sya << 16)); }
-            if (tid < 256) c.mru2[tid] = v4_mru_state(c, w, Wn - 1, (uint32_t) tid);
+            if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); s_wsym[warp] = (int) sy; s_wsya[warp] = (int) sya; }
             __syncthreads();
-            int tb = s_nt, lb = s_nl, ttot = 0, ltot = 0, stot = 0, satot = 0;
-            for (int w2 = 0; w2 < kV4W / 32; w2++) {
-                const int tw = s_wtok[w2], lw = s_wlit[w2];
-                if (w2 < warp) { tb += tw; lb += lw; }
-                ttot += tw; ltot += lw; stot += s_wsym[w2] & 0xffff; satot += s_wsym[w2] >> 16;
-            }
+            if (tid < 256) {
+                uint32_t run = 0;
+                #pragma unroll 8
+                for (int w2 = 0; w2 < 32; w2++) { const uint32_t t = wcnt[w2 * 256 + tid]; wcnt[w2 * 256 + tid] = (uint16_t) run; run += t; }
+                wcnt[32 * 256 + tid] = (uint16_t) run;
+            } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
+            else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
+            else if (tid >= 512 && tid < 768) c.mru2[tid - 512] = v4_mru_state(c, w, Wn - 1, (uint32_t) (tid - 512));
+            __syncthreads();
+            c.rank[tid] = valid ? (uint16_t) (wcnt[warp * 256 + ctx] + inwarp) : (uint16_t) 0;
+            if (tid < 2) { const uint32_t k2 = c.key[kV4W + tid]; c.rank[kV4W + tid] = (k2 & kV4KeyInvalid) ? (uint16_t) 0 : wcnt[32 * 256 + v4_ctx_of(k2)]; }
+            __syncthreads();
+            uint32_t suffix = 0;
+            if (marked) suffix = v4_claim_slot(c, tid);
+            __syncthreads();
             if (marked) {
-                const int ti = tb + __popc(bt & v4_lt_mask(lane));
+                v4_apply_position(c, lo, tid, suffix);
+                const int ti = s_nt + s_wtok[warp] + __popc(bt & v4_lt_mask(lane));
                 c.tok[ti] = v4_token_of(c, lo, tid);
-                if (islit) c.lit[lb + __popc(bl & v4_lt_mask(lane))] = (uint32_t) ti;
+                if (islit) c.lit[s_nl + s_wlit[warp] + __popc(bl & v4_lt_mask(lane))] = (uint32_t) ti;
                 if (w.rpos >= 0 && lo + tid == w.rpos) s_rpos_nt = ti;
             }
-            if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += wcnt[32 * 256 + tid]; }
             __syncthreads();
+            if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += wcnt[32 * 256 + tid]; }
             if (tid == 0) {
                 V4Run r = s_run;
                 if (w.rpos >= 0) {                                       // sub-block full (lz.cpp:153): close it, open the next
                     v4_close_subblock(c, r, w.rpos, s_op_at_rpos, s_rpos_nt);
                     r.j++; r.level = w.level2; r.tok_begin = s_rpos_nt; r.enc_begin = w.rpos;
-                    r.op = satot;
+                    r.op = s_wsya[32];
                 } else {
-                    r.op += stot;
+                    r.op += s_wsym[32];
                 }
                 r.ip = s_exit; r.skip_push = 0; r.prev_lit = v4_dec_kind(c.dec[s_lastrel]) == kV4Lit;
-                s_run = r; s_nt += ttot; s_nl += ltot;
+                s_run = r; s_nt += s_wtok[32]; s_nl += s_wlit[32];
             }
         }
         __syncthreads();

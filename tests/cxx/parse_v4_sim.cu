@@ -80,14 +80,15 @@ int main(int argc, char** argv) {
         // ---- SPEC
         for (int rel = 0; rel < kV4N; rel++) c.key[rel] = v4_key_of(c, lo + rel);
         memset(c.occ, 0, sizeof(uint32_t) * 256 * kV4Words);
-        for (int i = 0; i < kV4W + 3; i++) {                               // bit i of occ[b]: in[lo + i - 3] == b
+        for (int i = 0; i < kV4W + 4; i++) {                               // bit i of occ[b]: in[lo + i - 3] == b
             const int p = lo + i - 3;
             if (p < 0) continue;
             const uint32_t b = v4_rb8(c.rbw, (uint32_t) p);
             c.occ[b * kV4Words + (i >> 5)] |= 1u << (i & 31);
         }
+        for (int cq = 0; cq < 256; cq++) { uint32_t n = 0; for (int wq = 0; wq < kV4Words - 1; wq++) n += (uint32_t) z4_popc(v4_ctxbits(c, (uint32_t) cq, wq)); c.pcnt[cq] = (uint16_t) n; }
         v4_bucket_pass_serial(c);
-        for (int rel = 0; rel < kV4N; rel++) v4_link_position(c, lo, rel);
+        for (int rel = 0; rel < kV4N; rel++) v4_link_position(c, rel);
         for (int rel = 0; rel < kV4N; rel++) v4_spec_position(c, lo, rel);
         for (int rel = 0; rel < kV4W; rel++) v4_frozen_position(c, lo, rel, r.level);
         V4Win w; w.lo = lo; w.wend = wend; w.entry = r.ip; w.level = r.level; w.rpos = -1; w.level2 = r.level;
