@@ -43,7 +43,8 @@ typedef enum {
     ZLB_E_CUDA      = -3,   /* a CUDA runtime call or kernel failed; see zlb_last_error() */
     ZLB_E_NOMEM     = -4,   /* host or device allocation failed */
     ZLB_E_OVERFLOW  = -5,   /* caller's output buffer too small */
-    ZLB_E_FORMAT    = -6    /* malformed compressed stream (where the reference throws std::runtime_error) */
+    ZLB_E_FORMAT    = -6,   /* malformed compressed stream (where the reference throws std::runtime_error) */
+    ZLB_E_NCCL      = -7    /* NCCL unavailable (libnccl.so.2 could not be loaded) or an NCCL call failed */
 } zlb_status;
 
 typedef struct zlb_ctx     zlb_ctx;      /* one per (process, GPU): device buffers, streams */
@@ -92,6 +93,43 @@ int zlb_encode_complete(zlb_encoder* enc, uint8_t* out, size_t out_cap, size_t* 
 /* carried state: 65536 bytes of MTF tables (context-major, rank -> byte) followed by int32 LE current level */
 int zlb_encoder_get_state(zlb_encoder* enc, uint8_t* state /* ZLB_STATE_BYTES */);
 int zlb_encoder_set_state(zlb_encoder* enc, const uint8_t* state);
+
+/* ---- multi-GPU: ONE stream over several GPUs, one process per GPU ---------------------------------------
+ * The reference has no counterpart (it is single-threaded); what these calls move between GPUs is exactly the state the
+ * reference keeps outside its block loop: m_mtf[256] (src/libzling_lz.h:105, never reset) and current_level
+ * (src/libzling.cpp:185,261-266).  NCCL (libnccl.so.2) is loaded at run time on first use.
+ *   zlb_comm_get_unique_id   rank 0 makes the id; the caller distributes it to all ranks (any transport)
+ *   zlb_comm_create          ncclCommInitRank on the context's GPU; collective over all ranks
+ *   zlb_encode_stream_sharded  rank r owns a contiguous range of 16 MiB blocks of the stream (ranges in rank order;
+ *        `in`/`n` = this rank's range, n a multiple of ZLB_BLOCK_BYTES except on the last non-empty rank, n = 0 allowed).
+ *        Every rank parses its range at once; the 65 540-byte carried state travels GPU -> GPU in block order
+ *        (ncclRecv from rank-1, ncclSend to rank+1, device buffers); MTF ranks + Huffman + framing of a range run when
+ *        its carried state has arrived; ONE variable-length gather (sizes: ncclAllGather of u64; payloads: one group of
+ *        ncclSend/ncclRecv) brings the framed bytes to rank 0, which copies the whole stream to `out` (host; may be
+ *        NULL on the other ranks).  *out_len = total stream bytes on rank 0, this rank's framed bytes elsewhere.
+ *        Collective: every rank of the communicator must call it.  The bytes equal zlb_encode_blocks on one GPU.
+ *   zlb_encode_blocks_gathered  independent streams, one per rank (zlb_encode_blocks on every rank), whose framed outputs stay
+ *        in device memory and reach rank 0 through the same single gather: `out` on rank 0 = the streams back to back in
+ *        rank order, sizes[r] = bytes of rank r's stream
+ *   zlb_gather_packed        the gather alone, for outputs already in device memory */
+#define ZLB_COMM_ID_BYTES 128
+typedef struct zlb_comm zlb_comm;
+typedef struct {
+    double   ms_wait_carry;   /* exchange stream: from the parse launch to the arrival of the previous range's state */
+    double   ms_gather;       /* sizes + payload gather (+ D2H of the whole stream on rank 0) */
+    uint64_t local_bytes;     /* framed bytes of this rank's range */
+    uint64_t total_bytes;     /* framed bytes of the whole stream */
+} zlb_shard_stats;
+int       zlb_comm_get_unique_id(uint8_t* id /* ZLB_COMM_ID_BYTES */);
+zlb_comm* zlb_comm_create(zlb_ctx* ctx, int rank, int world, const uint8_t* id /* ZLB_COMM_ID_BYTES */);
+void      zlb_comm_destroy(zlb_comm* comm);
+int       zlb_comm_get_stats(const zlb_comm* comm, zlb_shard_stats* out);
+int zlb_encode_stream_sharded(zlb_encoder* enc, zlb_comm* comm, const uint8_t* in, size_t n, int in_on_device,
+                              uint8_t* out, size_t out_cap, size_t* out_len);
+int zlb_encode_blocks_gathered(zlb_encoder* enc, zlb_comm* comm, const uint8_t* in, size_t n, int in_on_device,
+                               uint8_t* out, size_t out_cap, size_t* out_len, uint64_t* sizes /* [world], may be NULL */);
+int zlb_gather_packed(zlb_comm* comm, const uint8_t* d_local, size_t n_local, uint8_t* out, size_t out_cap, size_t* out_len,
+                      uint64_t* sizes /* [world], may be NULL */);
 
 /* ---- decode ------------------------------------------------------------------------------------------ */
 zlb_decoder* zlb_decoder_begin(zlb_ctx* ctx);

@@ -5,4 +5,4 @@
   api.py       ctypes binding of the C ABI
   corpus.py    seeded synthetic inputs of BASELINE.json's configs
 """
-from .api import Context, Encoder, Decoder, PinnedBuffer, ZlingError, FormatError, load, lib_path, EXPORTS, BLOCK  # noqa: F401
+from .api import Context, Encoder, Decoder, Comm, PinnedBuffer, ZlingError, FormatError, load, lib_path, EXPORTS, BLOCK  # noqa: F401

@@ -32,6 +32,13 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ShardStats(C.Structure):
+    _fields_ = [("ms_wait_carry", C.c_double), ("ms_gather", C.c_double), ("local_bytes", C.c_uint64), ("total_bytes", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class SubBlock(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("tok_begin", "tok_end", "enc_begin", "enc_end", "rlen", "level", "olen", "bits_lo")]
 
@@ -40,7 +47,8 @@ EXPORTS = ["zlb_device_count", "zlb_create", "zlb_destroy", "zlb_max_blocks", "z
            "zlb_host_alloc", "zlb_host_free", "zlb_encode_bound", "zlb_encoder_begin", "zlb_encoder_end",
            "zlb_encode_blocks", "zlb_encode_blocks_device", "zlb_encode_submit", "zlb_encode_complete", "zlb_encoder_get_state", "zlb_encoder_set_state",
            "zlb_decoder_begin", "zlb_decoder_end", "zlb_decode_blocks", "zlb_get_stats", "zlb_debug_tokens",
-           "zlb_debug_subblocks", "zlb_debug_huff_tables"]
+           "zlb_debug_subblocks", "zlb_debug_huff_tables",
+           "zlb_comm_get_unique_id", "zlb_comm_create", "zlb_comm_destroy", "zlb_comm_get_stats", "zlb_encode_stream_sharded", "zlb_encode_blocks_gathered", "zlb_gather_packed"]
 
 _lib = None
 
@@ -86,6 +94,14 @@ def load():
     L.zlb_debug_tokens.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint32), C.c_size_t, C.POINTER(C.c_size_t)]
     L.zlb_debug_subblocks.argtypes = [C.c_void_p, C.c_int, C.POINTER(SubBlock), C.c_size_t, C.POINTER(C.c_size_t)]
     L.zlb_debug_huff_tables.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int, _u8p, C.POINTER(C.c_uint16)]
+    L.zlb_comm_get_unique_id.argtypes = [_u8p]
+    L.zlb_comm_create.restype = C.c_void_p
+    L.zlb_comm_create.argtypes = [C.c_void_p, C.c_int, C.c_int, _u8p]
+    L.zlb_comm_destroy.argtypes = [C.c_void_p]
+    L.zlb_comm_get_stats.argtypes = [C.c_void_p, C.POINTER(ShardStats)]
+    L.zlb_encode_stream_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.zlb_encode_blocks_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+    L.zlb_gather_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -282,6 +298,69 @@ class Encoder:
         s = np.ascontiguousarray(s, dtype=np.uint8)
         assert s.size == 65540
         _check(load().zlb_encoder_set_state(self._h, s.ctypes.data_as(_u8p)))
+
+
+class Comm:
+    """NCCL communicator of the ranks that share ONE stream (zlb_comm): one process per GPU.  `bcast(id_bytes)` must
+    return rank 0's 128-byte id on every rank (e.g. a torch.distributed broadcast, an MPI bcast, a file)."""
+
+    def __init__(self, ctx, rank, world, bcast):
+        L = load()
+        idb = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _check(L.zlb_comm_get_unique_id(idb.ctypes.data_as(_u8p)))
+        idb = np.ascontiguousarray(bcast(idb), dtype=np.uint8)
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self._h = L.zlb_comm_create(ctx._h, rank, world, idb.ctypes.data_as(_u8p))
+        if not self._h:
+            raise ZlingError(L.zlb_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().zlb_comm_destroy(self._h)
+            self._h = None
+
+    def stats(self):
+        s = ShardStats()
+        _check(load().zlb_comm_get_stats(self._h, C.byref(s)))
+        return s.asdict()
+
+    def encode_stream(self, enc, shard, out=None, device_ptr=None):
+        """this rank's block range of ONE stream (host array, or a device pointer + shard = byte count); on rank 0 `out`
+        (a host uint8 array) receives the whole framed stream.  Returns the byte count (total on rank 0, local elsewhere)."""
+        n = C.c_size_t(0)
+        if device_ptr is not None:
+            ptr, size, on_dev = device_ptr, int(shard), 1
+        else:
+            a = _as_u8(shard)
+            self._keep = a
+            ptr, size, on_dev = a.ctypes.data, a.size, 0
+        _check(load().zlb_encode_stream_sharded(enc._h, self._h, ptr, size, on_dev, out.ctypes.data if out is not None else None,
+                                                out.size if out is not None else 0, C.byref(n)))
+        return n.value
+
+    def encode_gathered(self, enc, data, out=None, device_ptr=None):
+        """independent streams, one per rank: encode this rank's stream and gather all framed streams on rank 0 (one NCCL
+        gather, device to device); returns (bytes, sizes) — bytes = total on rank 0, local elsewhere"""
+        n = C.c_size_t(0)
+        sizes = (C.c_uint64 * self.world)()
+        if device_ptr is not None:
+            ptr, size, on_dev = device_ptr, int(data), 1
+        else:
+            a = _as_u8(data)
+            self._keep = a
+            ptr, size, on_dev = a.ctypes.data, a.size, 0
+        _check(load().zlb_encode_blocks_gathered(enc._h, self._h, ptr, size, on_dev, out.ctypes.data if out is not None else None,
+                                                 out.size if out is not None else 0, C.byref(n), sizes))
+        return n.value, list(sizes)
+
+    def gather_packed(self, d_ptr, nbytes, out=None):
+        """independent streams per rank: one gather of the packed outputs (device memory) to rank 0; returns (total, sizes)"""
+        n = C.c_size_t(0)
+        sizes = (C.c_uint64 * self.world)()
+        _check(load().zlb_gather_packed(self._h, d_ptr, nbytes, out.ctypes.data if out is not None else None,
+                                        out.size if out is not None else 0, C.byref(n), sizes))
+        return n.value, list(sizes)
 
 
 class Decoder:

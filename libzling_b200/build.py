@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzling.so")
 SOURCES = ["zl_engine.cu", "zl_api.cpp"]
-DEPS = SOURCES + ["zl_kernels.cu", "zl_mtf_walk.h", "zl_kernels.cuh", "zl_parse_v2.cuh", "zl_parse_v3.cuh", "zl_parse_v4.cuh", "zl_tables.h", "../../include/zlb.h",
+DEPS = SOURCES + ["zl_kernels.cu", "zl_shard.cuh", "zl_mtf_walk.h", "zl_kernels.cuh", "zl_parse_v2.cuh", "zl_parse_v3.cuh", "zl_parse_v4.cuh", "zl_tables.h", "../../include/zlb.h",
                   "../../include/libzling/libzling.h", "../../include/libzling/libzling_utils.h"]
 
 

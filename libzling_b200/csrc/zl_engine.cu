@@ -20,6 +20,7 @@
 #include "zl_kernels.cuh"
 
 #include "zl_kernels.cu"      // single translation unit: kernels + engine
+#include "zl_shard.cuh"
 
 using namespace zl;
 
@@ -541,6 +542,239 @@ int zlb_encode_complete(zlb_encoder* e, uint8_t* out, size_t out_cap, size_t* ou
     finish_stats(c, true);
     *out_len = produced;
     e->cur ^= 1; e->cur_level = level_after;
+    return ZLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU
+struct zlb_comm {
+    zlb_ctx* ctx = nullptr;
+    ncclComm_t nccl = nullptr;
+    int rank = 0, world = 1;
+    cudaStream_t stream = nullptr;          // exchange stream: the carry can arrive while the parse kernel runs on ctx->stream
+    uint8_t* d_carry = nullptr;             // ZLB_STATE_BYTES (MTF tables + int32 level), padded
+    unsigned long long* d_sizes = nullptr;  // [world + 1]: [world] = this rank's size (all-gather input)
+    unsigned long long* h_sizes = nullptr;  // pinned mirror, [world + 1]
+    int32_t* h_level = nullptr;             // pinned
+    uint8_t* d_all = nullptr;               // rank 0: the gathered stream
+    size_t all_cap = 0;
+    cudaEvent_t ev[4] = {};
+    zlb_shard_stats stats = {};
+};
+#define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    snprintf(g_err, sizeof g_err, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString ? nccl_api().GetErrorString(r_) : "?", __FILE__, __LINE__); return ZLB_E_NCCL; } } while (0)
+
+int zlb_comm_get_unique_id(uint8_t* id) {
+    if (!id) return fail(ZLB_E_ARG, "zlb_comm_get_unique_id: null argument");
+    NcclApi& n = nccl_api();
+    if (!n.lib) return fail(ZLB_E_NCCL, "zlb_comm_get_unique_id: %s", n.error ? n.error : "NCCL unavailable");
+    static_assert(sizeof(ncclUniqueId) == ZLB_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    NC(n.GetUniqueId(&u));
+    memcpy(id, &u, sizeof u);
+    return ZLB_OK;
+}
+void zlb_comm_destroy(zlb_comm* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->nccl && nccl_api().CommDestroy) nccl_api().CommDestroy(m->nccl);
+    cudaFree(m->d_carry); cudaFree(m->d_sizes); cudaFree(m->d_all);
+    if (m->h_sizes) cudaFreeHost(m->h_sizes);
+    if (m->h_level) cudaFreeHost(m->h_level);
+    for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+zlb_comm* zlb_comm_create(zlb_ctx* c, int rank, int world, const uint8_t* id) {
+    if (!c || !id || world < 1 || rank < 0 || rank >= world) { fail(ZLB_E_ARG, "zlb_comm_create: bad argument"); return nullptr; }
+    NcclApi& n = nccl_api();
+    if (!n.lib) { fail(ZLB_E_NCCL, "zlb_comm_create: %s", n.error ? n.error : "NCCL unavailable"); return nullptr; }
+    if (cudaSetDevice(c->device) != cudaSuccess) { fail(ZLB_E_CUDA, "zlb_comm_create: cudaSetDevice failed"); return nullptr; }
+    zlb_comm* m = new (std::nothrow) zlb_comm();
+    if (!m) { fail(ZLB_E_NOMEM, "zlb_comm_create: out of host memory"); return nullptr; }
+    m->ctx = c; m->rank = rank; m->world = world;
+    ncclUniqueId u; memcpy(&u, id, sizeof u);
+    bool ok = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&m->d_carry, ZLB_STATE_BYTES + 60) == cudaSuccess &&
+              cudaMalloc(&m->d_sizes, ((size_t) world + 1) * 8) == cudaSuccess &&
+              cudaHostAlloc(&m->h_sizes, ((size_t) world + 1) * 8, cudaHostAllocDefault) == cudaSuccess &&
+              cudaHostAlloc(&m->h_level, 64, cudaHostAllocDefault) == cudaSuccess;
+    for (auto& e : m->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    if (!ok) { fail(ZLB_E_CUDA, "zlb_comm_create: device allocation failed"); cudaGetLastError(); zlb_comm_destroy(m); return nullptr; }
+    const ncclResult_t r = n.CommInitRank(&m->nccl, world, u, rank);
+    if (r != ncclSuccess) { fail(ZLB_E_NCCL, "zlb_comm_create: ncclCommInitRank failed: %s", n.GetErrorString(r)); m->nccl = nullptr; zlb_comm_destroy(m); return nullptr; }
+    return m;
+}
+int zlb_comm_get_stats(const zlb_comm* m, zlb_shard_stats* out) {
+    if (!m || !out) return fail(ZLB_E_ARG, "zlb_comm_get_stats: null argument");
+    *out = m->stats;
+    return ZLB_OK;
+}
+
+// all ranks: sizes by ONE all-gather of u64, payloads by ONE group of sends / receives; rank 0 ends up with every
+// rank's bytes back to back in m->d_all (block order = rank order) and the sizes in m->h_sizes[0..world)
+static int gather_packed(zlb_comm* m, const uint8_t* d_local, size_t n_local, size_t* total) {
+    NcclApi& n = nccl_api();
+    const int W = m->world;
+    m->h_sizes[W] = (unsigned long long) n_local;
+    CU(cudaMemcpyAsync(m->d_sizes + W, m->h_sizes + W, 8, cudaMemcpyHostToDevice, m->stream));
+    NC(n.AllGather(m->d_sizes + W, m->d_sizes, 1, ncclUint64, m->nccl, m->stream));
+    CU(cudaMemcpyAsync(m->h_sizes, m->d_sizes, (size_t) W * 8, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    size_t sum = 0;
+    for (int r = 0; r < W; r++) sum += (size_t) m->h_sizes[r];
+    *total = sum;
+    if (m->rank == 0) {
+        if (sum + 256 > m->all_cap) {
+            cudaFree(m->d_all); m->d_all = nullptr; m->all_cap = 0;
+            CU(cudaMalloc(&m->d_all, sum + sum / 8 + 4096));
+            m->all_cap = sum + sum / 8 + 4096;
+        }
+        if (n_local) CU(cudaMemcpyAsync(m->d_all, d_local, n_local, cudaMemcpyDeviceToDevice, m->stream));
+    }
+    if (W > 1) {
+        NC(n.GroupStart());
+        if (m->rank == 0) {
+            size_t off = (size_t) m->h_sizes[0];
+            for (int r = 1; r < W; r++) {
+                if (m->h_sizes[r]) NC(n.Recv(m->d_all + off, (size_t) m->h_sizes[r], ncclUint8, r, m->nccl, m->stream));
+                off += (size_t) m->h_sizes[r];
+            }
+        } else if (n_local) {
+            NC(n.Send(d_local, n_local, ncclUint8, 0, m->nccl, m->stream));
+        }
+        NC(n.GroupEnd());
+    }
+    return ZLB_OK;
+}
+
+int zlb_gather_packed(zlb_comm* m, const uint8_t* d_local, size_t n_local, uint8_t* out, size_t out_cap, size_t* out_len, uint64_t* sizes) {
+    if (!m || (n_local && !d_local)) return fail(ZLB_E_ARG, "zlb_gather_packed: null argument");
+    CU(cudaSetDevice(m->ctx->device));
+    size_t total = 0;
+    CU(cudaEventRecord(m->ev[2], m->stream));
+    const int rc = gather_packed(m, d_local, n_local, &total);
+    if (rc) return rc;
+    if (m->rank == 0 && out) {
+        if (total > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_gather_packed: output buffer too small");
+        if (total) CU(cudaMemcpyAsync(out, m->d_all, total, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CU(cudaEventRecord(m->ev[3], m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    { float t = 0; cudaEventElapsedTime(&t, m->ev[2], m->ev[3]); m->stats.ms_gather = t; }
+    if (out_len) *out_len = total;
+    if (sizes) for (int r = 0; r < m->world; r++) sizes[r] = m->h_sizes[r];
+    return ZLB_OK;
+}
+
+int zlb_encode_blocks_gathered(zlb_encoder* e, zlb_comm* m, const uint8_t* in, size_t n, int in_on_device, uint8_t* out, size_t out_cap, size_t* out_len, uint64_t* sizes) {
+    if (!e || !m || (n && !in) || e->ctx != m->ctx) return fail(ZLB_E_ARG, "zlb_encode_blocks_gathered: bad argument");
+    zlb_ctx* c = e->ctx;
+    int rc = check_encode_args(e, in, n, in, &n);
+    if (rc) return rc;
+    CU(cudaSetDevice(c->device));
+    if (out_len) *out_len = 0;
+    m->stats = zlb_shard_stats{};
+    size_t produced = 0;
+    if (n) {
+        int level_after = e->cur_level;
+        CU(cudaEventRecord(c->ev[EV_START], c->stream));
+        if (!in_on_device) {
+            CU(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemsetAsync(c->d_in + n, 0, 64, c->stream));
+        }
+        CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+        rc = encode_device(e, in_on_device ? in : c->d_in, n, c->d_out, c->out_cap, &produced, &level_after);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev[EV_END], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        finish_stats(c, true);
+        e->cur ^= 1; e->cur_level = level_after;
+    }
+    size_t total = 0;
+    CU(cudaEventRecord(m->ev[2], m->stream));
+    rc = gather_packed(m, c->d_out, produced, &total);
+    if (rc) return rc;
+    if (m->rank == 0 && out) {
+        if (total > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_blocks_gathered: output buffer too small");
+        if (total) CU(cudaMemcpyAsync(out, m->d_all, total, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CU(cudaEventRecord(m->ev[3], m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    { float t = 0; cudaEventElapsedTime(&t, m->ev[2], m->ev[3]); m->stats.ms_gather = t; }
+    m->stats.local_bytes = produced; m->stats.total_bytes = total;
+    if (out_len) *out_len = m->rank == 0 ? total : produced;
+    if (sizes) for (int r = 0; r < m->world; r++) sizes[r] = m->h_sizes[r];
+    return ZLB_OK;
+}
+
+int zlb_encode_stream_sharded(zlb_encoder* e, zlb_comm* m, const uint8_t* in, size_t n, int in_on_device, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!e || !m || (n && !in) || e->ctx != m->ctx) return fail(ZLB_E_ARG, "zlb_encode_stream_sharded: bad argument");
+    zlb_ctx* c = e->ctx;
+    if (c->pending) return fail(ZLB_E_ARG, "zlb_encode_stream_sharded: a submitted range is pending on this context");
+    if (n > (size_t) c->max_blocks * kBlockBytes) return fail(ZLB_E_ARG, "zlb_encode_stream_sharded: more than max_blocks blocks in this rank's range");
+    NcclApi& nc = nccl_api();
+    CU(cudaSetDevice(c->device));
+    if (out_len) *out_len = 0;
+    m->stats = zlb_shard_stats{};
+    const uint8_t* d_in = in_on_device ? in : c->d_in;
+    size_t produced = 0;
+    int level_after = e->cur_level;
+    // 1. this rank's range: H2D + parse launch (returns at once; assumes the carried level is the requested one)
+    CU(cudaEventRecord(c->ev[EV_START], c->stream));
+    if (n) {
+        if (!in_on_device) {
+            CU(cudaMemcpyAsync(c->d_in, in, n, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemsetAsync(c->d_in + n, 0, 64, c->stream));
+        }
+        CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
+        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SUBMIT);
+        if (rc) return rc;
+    }
+    // 2. the carried state of the previous range, GPU -> GPU, while the parse runs
+    CU(cudaEventRecord(m->ev[0], m->stream));
+    if (m->rank > 0) {
+        NC(nc.Recv(m->d_carry, ZLB_STATE_BYTES, ncclUint8, m->rank - 1, m->nccl, m->stream));
+        CU(cudaMemcpyAsync(e->d_state[e->cur], m->d_carry, 65536, cudaMemcpyDeviceToDevice, m->stream));
+        CU(cudaMemcpyAsync(m->h_level, m->d_carry + 65536, 4, cudaMemcpyDeviceToHost, m->stream));
+        CU(cudaEventRecord(m->ev[1], m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        if (*m->h_level < 0 || *m->h_level > 4) return fail(ZLB_E_NCCL, "zlb_encode_stream_sharded: received a corrupt carried state");
+        e->cur_level = *m->h_level;
+        { float t = 0; cudaEventElapsedTime(&t, m->ev[0], m->ev[1]); m->stats.ms_wait_carry = t; }
+    }
+    // 3. MTF ranks + Huffman + framing of the range (re-parses its first block only if the carried level differs)
+    if (n) {
+        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_COMPLETE);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev[EV_END], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        finish_stats(c, true);
+        e->cur ^= 1; e->cur_level = level_after;
+    }
+    // 4. forward this range's final state
+    if (m->rank + 1 < m->world) {
+        *m->h_level = (int32_t) e->cur_level;
+        CU(cudaMemcpyAsync(m->d_carry, e->d_state[e->cur], 65536, cudaMemcpyDeviceToDevice, m->stream));
+        CU(cudaMemcpyAsync(m->d_carry + 65536, m->h_level, 4, cudaMemcpyHostToDevice, m->stream));
+        NC(nc.Send(m->d_carry, ZLB_STATE_BYTES, ncclUint8, m->rank + 1, m->nccl, m->stream));
+    }
+    // 5. ONE gather of the framed ranges
+    size_t total = 0;
+    CU(cudaEventRecord(m->ev[2], m->stream));
+    const int rc = gather_packed(m, c->d_out, produced, &total);
+    if (rc) return rc;
+    if (m->rank == 0 && out) {
+        if (total > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_stream_sharded: output buffer too small");
+        if (total) CU(cudaMemcpyAsync(out, m->d_all, total, cudaMemcpyDeviceToHost, m->stream));
+    }
+    CU(cudaEventRecord(m->ev[3], m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    { float t = 0; cudaEventElapsedTime(&t, m->ev[2], m->ev[3]); m->stats.ms_gather = t; }
+    m->stats.local_bytes = produced; m->stats.total_bytes = total;
+    if (out_len) *out_len = m->rank == 0 ? total : produced;
     return ZLB_OK;
 }
 
