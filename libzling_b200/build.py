@@ -34,6 +34,8 @@ def build(force=False, verbose=False):
            "-Xcompiler", "-fPIC,-fvisibility=default", "-shared", "-cudart", "static", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if os.environ.get("ZL_V4_PROFILE"):       # profiling build: per-thread timers inside the parse kernel's decide step
+        cmd += ["-DZL_V4_PROFILE=1"]
     if os.environ.get("ZL_V3_PROD"):          # experiment knob: producer threads of the parse kernel (default in zl_parse_v3.cuh)
         cmd += ["-DZL_V3_PROD=" + os.environ["ZL_V3_PROD"]]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]

@@ -299,7 +299,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V4Layout lay = v4_layout(dmax, lmax);
             if (pass == 0) CU(cudaMemsetAsync(c->d_v4c, 0, sizeof(V4Counters), st));
-            zl_rolz_parse_v4_kernel<<<nb, kV4W, lay.total, st>>>(pa, dmax, lmax, e->level, c->d_v4c);
+            zl_rolz_parse_v4_kernel<<<nb, kV4T, lay.total, st>>>(pa, dmax, lmax, e->level, c->d_v4c);
         } else if (c->parse_version == 3) {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V3Layout lay = v3_layout(dmax, lmax);
@@ -420,6 +420,11 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         c->stats.cyc_spec = c->h_v4c.cyc_spec; c->stats.cyc_resolve = c->h_v4c.cyc_rounds; c->stats.cyc_final = c->h_v4c.cyc_final;
         c->stats.cyc_total = c->h_v4c.cyc_total; c->stats.cyc_orbit = c->h_v4c.cyc_orbit; c->stats.cyc_rank = c->h_v4c.cyc_rank;
         c->stats.cyc_decide = c->h_v4c.cyc_decide;
+        if (getenv("ZLB_V4_TRACE")) {
+            fprintf(stderr, "v4 phases (cycles per window, summed over blocks / windows):");
+            for (int i = 0; i < 24; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
+            fprintf(stderr, "\n");
+        }
     } else if (c->parse_version == 3) {
         CU(cudaMemcpyAsync(&c->h_v3c, c->d_v3c, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

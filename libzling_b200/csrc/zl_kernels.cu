@@ -401,24 +401,24 @@ constexpr int kMtfChunk = 256;                                    // literal rec
 __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const uint32_t* lbuf_all, const uint32_t* ctx_off, int first_block, int nblocks,
                                                         const uint8_t* state_in, uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
     const int ctx = blockIdx.x, lane = threadIdx.x;
-    __shared__ __align__(16) uint8_t s_sym[256];          // rank -> byte
+    __shared__ __align__(16) uint16_t s_S[256];           // rank -> byte | mtf_next(rank) << 8   (zl_mtf_walk.h)
     __shared__ __align__(16) uint16_t s_R[256];           // byte -> rank | mtf_next(rank) << 8
     __shared__ __align__(16) uint32_t s_rec[2][kMtfChunk];
-    __shared__ __align__(16) uint8_t s_out[kMtfChunk];
+    __shared__ __align__(16) uint8_t s_out[kMtfChunk + 16];
     __shared__ __align__(16) uint8_t s_byte[2][kMtfChunk + 16];
-    __shared__ __align__(16) uint8_t s_next[256];         // mtf_next() as a table: one load instead of a multiply-divide chain
-    for (int i = lane; i < 256; i += 32) s_next[i] = (uint8_t) mtf_next(i);
     {
         const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
-        for (int i = lane; i < 256; i += 32) s_sym[i] = src[i];
-        __syncwarp();
-        for (int i = lane; i < 256; i += 32) s_R[s_sym[i]] = (uint16_t) (i | (mtf_next(i) << 8));
+        for (int i = lane; i < 256; i += 32) {
+            const uint32_t sy = src[i], nx = (uint32_t) mtf_next(i);
+            s_S[i] = (uint16_t) (sy | (nx << 8));
+            s_R[sy] = (uint16_t) ((uint32_t) i | (nx << 8));
+        }
         __syncwarp();
     }
     for (int b = first_block; b < nblocks; b++) {
         {   // MTF state at the start of block b (replay point for level-feedback re-parses)
             uint8_t* dst = checkpoints + (size_t) b * 65536 + ctx * 256;
-            for (int i = lane; i < 256; i += 32) dst[i] = s_sym[i];
+            for (int i = lane; i < 256; i += 32) dst[i] = (uint8_t) s_S[i];
         }
         const uint32_t lo = ctx_off[(size_t) b * 257 + ctx], hi = ctx_off[(size_t) b * 257 + ctx + 1];
         const uint32_t* list = lbuf_all + (size_t) b * kLitStride + lo;
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
             for (int q = 0; q < kMtfChunk / 32; q++) { const int i = base + kMtfChunk + q * 32 + lane; pre[q] = i < n ? list[i] : 0; }
             __syncwarp();
             const int cnt = min(kMtfChunk, n - base);
-            if (lane == 0) mtf_walk(s_R, s_sym, s_next, s_byte[buf], s_out, cnt);   // the serial chain: zl_mtf_walk.h
+            if (lane == 0) mtf_walk(s_R, s_S, s_byte[buf], s_out, cnt);           // the serial chain: zl_mtf_walk.h
             __syncwarp();
             for (int q = lane; q < cnt; q += 32) {
                 const uint32_t rec = s_rec[buf][q];
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
         }
     }
     __syncwarp();
-    for (int i = lane; i < 256; i += 32) state_out[ctx * 256 + i] = s_sym[i];
+    for (int i = lane; i < 256; i += 32) state_out[ctx * 256 + i] = (uint8_t) s_S[i];
 }
 
 // =====================================================================================================

@@ -29,15 +29,16 @@
 
 namespace zl {
 
-#ifndef ZL_V4_W
-#define ZL_V4_W 1024
+#ifndef ZL_V4_T
+#define ZL_V4_T 1024
 #endif
-constexpr int kV4W       = ZL_V4_W;             // main positions per window = threads per CTA
-constexpr int kV4N       = kV4W + 2;            // + two lazy look-ahead positions (records only)
+constexpr int kV4T       = ZL_V4_T;             // threads per CTA = positions with a record per window (a multiple of 128)
+constexpr int kV4N       = kV4T;                // positions with a record: the main ones + two lazy look-ahead positions
+constexpr int kV4W       = kV4N - 2;            // main positions per window (the window stride)
 constexpr int kV4R       = 2048;                // byte ring: >= 4 + kV4N + 264 + 16
 constexpr int kV4Tail    = 288;                 // bytes staged past the last look-ahead position
 constexpr int kV4Buckets = 4096;                // buckets of the link builder
-constexpr int kV4Words   = (kV4W + 3 + 31) / 32 + 1;  // bitset words over window positions (+3: push contexts start 3 bytes early; +1 word: funnel reads)
+constexpr int kV4Words   = (kV4N + 2 + 31) / 32 + 1;  // bitset words over window positions (+2: contexts of the last positions; +1 word: funnel reads)
 constexpr uint32_t kV4KeyInvalid = 0x80000000u; // position cannot be probed (first two bytes / last 273 bytes of the block)
 constexpr uint32_t kV4KeyMask    = 0x1fffffu;   // (context << 13) | hash slot
 constexpr uint32_t kV4Auto       = 0xffu;       // plan entry: predict the level (see v4_next_level)
@@ -123,14 +124,13 @@ ZL_HD uint32_t z4_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------------
 struct V4Layout {
     int dmax, lmax;
-    int rb, key, link, blink, pcnt, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
+    int rb, key, link, blink, pcnt, occw, mcnt, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
     int scratch_bytes;
 };
 // scratch is a union: SPEC uses it for the link builder's bucket tables, the rounds for the orbit / rank tables
 constexpr int kV4Groups      = 8;                                          // link builder: position groups with their own bucket table
-constexpr int kV4Levels      = 11;                                         // orbit: jump tables J^(2^l), l < kV4Levels
 constexpr int kV4ScratchSpec = kV4Groups * kV4Buckets * 2;
-constexpr int kV4ScratchRnd  = kV4Levels * ((kV4N * 2 + 15) & ~15) + 33 * 256 * 2;
+constexpr int kV4ScratchRnd  = 4096 + 33 * 256 * 2;
 __host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
     V4Layout L; L.dmax = dmax; L.lmax = lmax;
     int at = 0;
@@ -139,7 +139,9 @@ __host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
     L.key   = take(4 * kV4N);
     L.link  = take(2 * kV4N);
     L.blink = take(2 * kV4N);
-    L.pcnt  = take(2 * 256);
+    L.pcnt  = take(4 * 256);
+    L.occw  = take(4 * 256);
+    L.mcnt  = take(4 * 256);
     L.hdr   = take(4 * kV4N);
     L.node  = take(4 * kV4N * dmax);
     L.nodeq = take(4 * kV4N * lmax);
@@ -169,11 +171,13 @@ struct V4Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory (indexed by rel = x - lo unless noted)
     uint32_t* rbw;                              // input bytes: ring of kV4R bytes viewed as words, indexed by block position
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint16_t* pcnt; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* pcnt; uint32_t* occw; uint32_t* mcnt; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
     uint32_t* fdec; uint32_t* fx; uint16_t* rank; uint8_t* mark; uint8_t* plit; uint8_t* sup; uint32_t* dec; uint32_t* ndec;
     uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c;
                                                 // position lo + i - 2 has context c)
-    // pcnt[c] = positions of the window (incl. look-ahead) whose context byte is c: an upper bound of the inserts into c
+    // pcnt[c] = bytes of value c among in[lo - 3 .. lo + N - 2] (the set bits of occ[c]): an upper bound of the window positions
+    // whose context byte is c, i.e. of the inserts this window can make into context c
+    // occw[c]: bit w set <=> word w of occ[c] is not empty (w < 32);  mcnt[c] = MARKED positions whose context byte is c (per round)
     uint32_t* mbits;                            // [kV4Words]: bit i <=> position lo + i is a token start
     uint32_t* cnt; uint32_t* mru; uint32_t* mru2;   // carried: inserts per context before the window, word MRU at the window's entry
     uint32_t* last;                             // host replay only: bucket table of the serial link builder
@@ -181,7 +185,7 @@ struct V4Ctx {
 };
 __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint16_t*) (smem + L.pcnt); c.hdr = (uint32_t*) (smem + L.hdr);
+    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint32_t*) (smem + L.pcnt); c.occw = (uint32_t*) (smem + L.occw); c.mcnt = (uint32_t*) (smem + L.mcnt); c.hdr = (uint32_t*) (smem + L.hdr);
     c.node = (uint32_t*) (smem + L.node); c.nodeq = (uint32_t*) (smem + L.nodeq); c.fdec = (uint32_t*) (smem + L.fdec);
     c.fx = (uint32_t*) (smem + L.fx); c.rank = (uint16_t*) (smem + L.rank); c.mark = smem + L.mark; c.plit = smem + L.plit;
     c.sup = smem + L.sup; c.dec = (uint32_t*) (smem + L.dec); c.ndec = (uint32_t*) (smem + L.ndec);
@@ -253,47 +257,51 @@ inline void v4_bucket_pass_serial(const V4Ctx& c) {
     }
 }
 
-// exact GetCommonLength (lz.cpp:66-89) with both operands inside the byte ring
+// exact GetCommonLength (lz.cpp:66-89) with both operands inside the byte ring: aligned words of both sides, eight at a time
 ZL_HD int v4_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q) {
     if (v4_rb32(rbw, p) != v4_rb32(rbw, q)) return 0;
-    for (int n = 4; n < 256; n += 4) {
-        const uint32_t d = v4_rb32(rbw, p + n) ^ v4_rb32(rbw, q + n);
-        if (d) return n + ((z4_ffs(d) - 1) >> 3);
+    for (int n = 4; n < 272; n += 32) {
+        const uint32_t pa = p + (uint32_t) n, qa = q + (uint32_t) n;
+        const uint32_t shp = (pa & 3u) * 8u, shq = (qa & 3u) * 8u, pi = pa >> 2, qi = qa >> 2;
+        uint32_t pw[9], qw[9];
+        #pragma unroll
+        for (int i = 0; i <= 8; i++) { pw[i] = rbw[(pi + (uint32_t) i) & (kV4R / 4 - 1)]; qw[i] = rbw[(qi + (uint32_t) i) & (kV4R / 4 - 1)]; }
+        uint32_t fd = 0; int fi = 8;
+        #pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            const uint32_t d = z4_funnel(pw[i], pw[i + 1], shp) ^ z4_funnel(qw[i], qw[i + 1], shq);
+            if (d) { fd = d; fi = i; }
+        }
+        if (fd) { const int l = n + 4 * fi + ((z4_ffs(fd) - 1) >> 3); return l < kMaxLen ? l : kMaxLen; }
     }
-    const uint32_t d = v4_rb32(rbw, p + 256) ^ v4_rb32(rbw, q + 256);
-    const int t = d ? ((z4_ffs(d) - 1) >> 3) : 4;
-    return 256 + (t < 3 ? t : 3);
+    return kMaxLen;
 }
 // The same with the candidate q read from global memory (q < x, anywhere in the block).  The candidate's bytes come
-// in batches of aligned 16-byte loads issued together (one L2 round trip per batch instead of one per 4 bytes): 32
-// bytes first (most matches end there), then 80 at a time.
+// in batches of aligned 32-bit loads issued together (one L2 round trip per batch instead of one per 4 bytes): 16
+// bytes first (most matches end there), then 32 at a time.
 template <int NW>     // compare NW 32-bit words at offset n; returns the number of equal leading bytes (4 * NW if all agree)
 ZL_HD int v4_cmp_words(const V4Ctx& c, uint32_t x, uint32_t q, int n) {
-    constexpr int NV = NW / 4 + 1;
-    const uint4* qa = reinterpret_cast<const uint4*>(c.in + ((q + (uint32_t) n) & ~15u));
-    uint32_t qw[4 * NV + 1];
+    const uint32_t qa = q + (uint32_t) n, xa = x + (uint32_t) n;
+    const uint32_t* qp = reinterpret_cast<const uint32_t*>(c.in) + (qa >> 2);
+    const uint32_t shq = (qa & 3u) * 8u, shx = (xa & 3u) * 8u, xi = xa >> 2;
+    uint32_t qw[NW + 1], xw[NW + 1];
     #pragma unroll
-    for (int i = 0; i < NV; i++) { const uint4 v = z4_ld_in128(qa + i); qw[4 * i] = v.x; qw[4 * i + 1] = v.y; qw[4 * i + 2] = v.z; qw[4 * i + 3] = v.w; }
-    qw[4 * NV] = 0;
-    const uint32_t sh = ((q + (uint32_t) n) & 3u) * 8u, wo = ((q + (uint32_t) n) >> 2) & 3u;
-    int eq = 4 * NW;
+    for (int i = 0; i <= NW; i++) { qw[i] = z4_ld_in32(qp + i); xw[i] = c.rbw[(xi + (uint32_t) i) & (kV4R / 4 - 1)]; }
+    uint32_t fd = 0; int fi = NW;                                        // first differing word (scanning from the last one down)
     #pragma unroll
     for (int i = NW - 1; i >= 0; i--) {
-        // word i of the candidate starts at aligned word wo + i (wo = 0..3, selected without dynamic register indexing)
-        const uint32_t lo0 = wo == 0 ? qw[i] : wo == 1 ? qw[i + 1] : wo == 2 ? qw[i + 2] : qw[i + 3];
-        const uint32_t hi0 = wo == 0 ? qw[i + 1] : wo == 1 ? qw[i + 2] : wo == 2 ? qw[i + 3] : qw[i + 4];
-        const uint32_t d = z4_funnel(lo0, hi0, sh) ^ v4_rb32(c.rbw, x + (uint32_t) n + 4u * (uint32_t) i);
-        if (d) eq = 4 * i + ((z4_ffs(d) - 1) >> 3);
+        const uint32_t d = z4_funnel(qw[i], qw[i + 1], shq) ^ z4_funnel(xw[i], xw[i + 1], shx);
+        if (d) { fd = d; fi = i; }
     }
-    return eq;
+    return fd ? 4 * fi + ((z4_ffs(fd) - 1) >> 3) : 4 * NW;
 }
 ZL_HD int v4_common_len_mixed(const V4Ctx& c, uint32_t x, uint32_t q) {
-    int e = v4_cmp_words<8>(c, x, q, 0);
+    int e = v4_cmp_words<4>(c, x, q, 0);
     if (e < 4) return 0;
-    if (e < 32) return e;
-    for (int n = 32; n < 240; n += 80) {
-        e = v4_cmp_words<20>(c, x, q, n);
-        if (e < 80) { const int l = n + e; return l < kMaxLen ? l : kMaxLen; }
+    if (e < 16) return e;
+    for (int n = 16; n < 272; n += 32) {
+        e = v4_cmp_words<8>(c, x, q, n);
+        if (e < 32) { const int l = n + e; return l < kMaxLen ? l : kMaxLen; }
     }
     return kMaxLen;                                                      // 272 bytes agree; the length is capped at 259
 }
@@ -445,7 +453,9 @@ ZL_HD int v4_valid_nodes(const V4Ctx& c, int rel, int nvis, uint32_t head_b, uin
 }
 // Could a slot read by the record of rel have been overwritten by this window's inserts?  (static bound: pcnt)
 ZL_HD bool v4_maybe_stale(const V4Ctx& c, int rel, uint32_t hdr, uint32_t extra) {
-    return (hdr & 31u) && (hdr >> 5) + 1u <= (uint32_t) c.pcnt[v4_ctx_of(c.key[rel])] + extra;
+    const uint32_t cq = v4_ctx_of(c.key[rel]);
+    const uint32_t a = c.pcnt[cq], b = c.mcnt[cq] + 1u;                  // inserts into cq so far <= positions with that context, <= marked ones + the one being decided
+    return (hdr & 31u) && (hdr >> 5) + 1u <= (a < b ? a : b) + extra;
 }
 // slot head seen by the insert at y: the nearest marked same-key position before it, else the frozen head
 ZL_HD uint32_t v4_suffix_live(const V4Ctx& c, int y) {
@@ -673,10 +683,14 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
     // pushes newest first: (a1,u1), (a2,u2), ...; the state is that after the newest EFFECTIVE push j: (a_j, front before j)
     bool have = false;                // a push whose effectiveness is still unknown (needs the front before it)
     uint32_t a = 0; bool u = false;
-    int wi = xrel >> 5;
-    uint32_t m = occ[wi] & c.mbits[wi] & (0xffffffffu >> (31 - (xrel & 31)));
-    const int wlo = elo >> 5;
-    while (true) {
+    const int whi = xrel >> 5, wlo = elo >> 5;
+    // words of the window that hold a byte cq at all (occw), between the first possible push and xrel, newest first
+    uint32_t words = c.occw[cq] & (0xffffffffu >> (31 - whi)) & (0xffffffffu << wlo);
+    while (words) {
+        const int wi = 31 - z4_clz(words);
+        words &= ~(1u << wi);
+        uint32_t m = occ[wi] & c.mbits[wi];
+        if (wi == whi) m &= 0xffffffffu >> (31 - (xrel & 31));
         if (wi == wlo) m &= 0xffffffffu << (elo & 31);
         while (m) {
             const int b = 31 - z4_clz(m);
@@ -690,9 +704,6 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
             }
             have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
         }
-        if (wi == wlo) break;
-        wi--;
-        m = occ[wi] & c.mbits[wi];
     }
     if (!have) return base;
     if (u || (base & 0xffffu) != a) return a | (base << 16);
@@ -700,20 +711,31 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
 }
 
 // ---- ROUNDS: the decision of a position given the marks --------------------------------------------------------------------
-ZL_HD uint32_t v4_decide(const V4Ctx& c, const V4Win& w, int rel) {
+#if defined(ZL_V4_PROFILE) && defined(__CUDA_ARCH__)
+#define V4_PROF_T() ((uint32_t) clock64())
+#else
+#define V4_PROF_T() 0u
+#endif
+ZL_HD uint32_t v4_decide(const V4Ctx& c, const V4Win& w, int rel, uint32_t* prof = nullptr) {
     const int x = w.lo + rel;
     const int level = (w.rpos >= 0 && x >= w.rpos) ? w.level2 : w.level;
     const uint32_t fd = c.fdec[rel], fxw = c.fx[rel];
     uint32_t len = fd & 511u, ref = (fd >> 18) & (kRing - 1);
-    if (level != w.level || v4_hazard(c, rel, fd, fxw, depth_lazy2(level))) {
+    const uint32_t p0 = V4_PROF_T();
+    const bool hz = level != w.level || v4_hazard(c, rel, fd, fxw, depth_lazy2(level));
+    const uint32_t p1 = V4_PROF_T();
+    if (hz) {
         uint32_t rf = 0;
         len = (uint32_t) v4_probe_general(c, w.lo, rel, level, &rf);
         ref = rf;
     }
+    const uint32_t p2 = V4_PROF_T();
+    if (prof) { prof[0] = p1 - p0; prof[1] = p2 - p1; prof[2] = 0; }
     if (len) return len | (kV4Match << 9) | (ref << 12);
     const uint32_t m = v4_mru_state(c, w, rel, v4_ctx_of(c.key[rel]));  // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
     const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
     const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
+    if (prof) prof[2] = V4_PROF_T() - p2;
     return kind << 9;
 }
 
@@ -811,9 +833,41 @@ ZL_HD void v4_resolve_tail(const V4Ctx& c, V4Run& r, int* nt_io, int* nl_io) {
 #if defined(__CUDACC__)
 namespace zl {
 
-struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide; };
+struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[24]; };
 
 __device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
+// Word MRU of context cq after all pushes of the window (the state carried into the next window): v4_mru_state(.., Wn - 1, cq)
+// evaluated by a whole warp, lane = bitset word; every lane returns the same value
+__device__ __forceinline__ uint32_t v4_mru_carry_warp(const V4Ctx& c, const V4Win& w, int Wn, uint32_t cq, int lane) {
+    uint32_t base = c.mru[cq];
+    int elo = w.entry - w.lo + (w.skip_push ? 1 : 0);
+    if (w.rpos >= 0) { base = 0; elo = w.rpos - w.lo + 1; }             // the window holds the roll-over: only later pushes count
+    const int xrel = Wn - 1;
+    if (xrel < elo) return base;
+    uint32_t m = c.occ[cq * kV4Words + lane] & c.mbits[lane];
+    if (lane == (xrel >> 5)) m &= 0xffffffffu >> (31 - (xrel & 31));
+    if (lane > (xrel >> 5)) m = 0;
+    if (lane == (elo >> 5)) m &= 0xffffffffu << (elo & 31);
+    if (lane < (elo >> 5)) m = 0;
+    bool have = false, u = false;
+    uint32_t a = 0;
+    while (true) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, m != 0);
+        if (!bal) break;
+        const int hw = 31 - __clz(bal);
+        const uint32_t mw = __shfl_sync(0xffffffffu, m, hw);
+        const int bq = 31 - __clz(mw);
+        if (lane == hw) m &= ~(1u << bq);
+        const int e = hw * 32 + bq;
+        const uint32_t xe = (uint32_t) (w.lo + e);
+        const uint32_t pw = (v4_rb8(c.rbw, xe - 2) << 8) | v4_rb8(c.rbw, xe - 1);
+        if (have && (u || pw != a)) return a | (pw << 16);
+        have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
+    }
+    if (!have) return base;
+    if (u || (base & 0xffffu) != a) return a | (base << 16);
+    return base;
+}
 // warp 0: per-warp totals arr[0..31] -> exclusive prefix in place, grand total in arr[32] (callers synchronise around it)
 __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
     const int v = arr[lane];
@@ -824,8 +878,8 @@ __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
     if (lane == 31) arr[32] = incl;
 }
 
-// ---- the kernel: grid = blocks of the batch, kV4W threads, thread t owns position lo + t of the current window -----------
-__global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int dmax, int lmax, int base_level, V4Counters* counters) {
+// ---- the kernel: grid = blocks of the batch, kV4T threads, thread t owns position lo + t of the current window -----------
+__global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int dmax, int lmax, int base_level, V4Counters* counters) {
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -833,6 +887,12 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ V4Win s_win;
     __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
     __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
+    __shared__ uint32_t s_dmax[4];
+    __shared__ unsigned long long s_ph[24];                                      // phase timers (thread 0's clock between barriers)
+    long long tprev = 0;
+#define V4_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); s_ph[i] += (unsigned long long) (now_ - tprev); tprev = now_; } } while (0)
+    if (tid < 24) s_ph[tid] = 0;
+    static_assert(kV4T == 1024, "the kernel assumes 32 warps (prefix helpers, wcnt rows, link groups)");
     const V4Layout L = v4_layout(dmax, lmax);
     V4Ctx c;
     v4_bind(c, smem_raw, L);
@@ -846,7 +906,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
     uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + 4096);                   // FINALIZE: [33][256] marked positions per (warp, context)
 
-    for (int i = tid; i < 256; i += kV4W) { c.cnt[i] = 0; c.mru[i] = 0; }
+    for (int i = tid; i < 256; i += kV4T) { c.cnt[i] = 0; c.mru[i] = 0; }
     long long cyc_spec = 0, cyc_rounds = 0, cyc_final = 0, cyc_orbit = 0, cyc_rank = 0, cyc_decide = 0;
     unsigned long long n_rounds = 0, n_windows = 0;
     const long long t_begin = clock64();
@@ -871,26 +931,28 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         const int wend = lo + kV4W < lim ? lo + kV4W : lim;
         const int Wn = wend - lo;
         const int hi = v4_stage_hi(k);
-        for (int src = staged_hi + tid * 16; src < hi; src += kV4W * 16) v4_stage16(c, src);
+        for (int src = staged_hi + tid * 16; src < hi; src += kV4T * 16) v4_stage16(c, src);
         staged_hi = hi;
         __syncthreads();
         if (s_run.ip >= wend) continue;                                  // no token starts in this window (uniform)
         const long long t0 = clock64();
+        tprev = t0;
         // ================================================= SPEC =================================================
         c.key[tid] = v4_key_of(c, lo + tid);
-        if (tid < 2) c.key[kV4W + tid] = v4_key_of(c, lo + kV4W + tid);
-        for (int i = tid; i < 256 * kV4Words; i += kV4W) c.occ[i] = 0;
-        { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4W) z[i] = make_uint4(0, 0, 0, 0); }
+        for (int i = tid; i < 256 * kV4Words; i += kV4T) c.occ[i] = 0;
+        if (tid < 256) { c.pcnt[tid] = 0; c.occw[tid] = 0; }
+        { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4T) z[i] = make_uint4(0, 0, 0, 0); }
         __syncthreads();
-        {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..3 also bits W..W+3
+        V4_TICK(0);
+        {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..1 also bits N, N+1
             const int p = lo + tid - 3;
             const uint32_t v = p >= 0 ? v4_rb8(c.rbw, (uint32_t) p) : 256u + (uint32_t) lane;
             const uint32_t grp = __match_any_sync(0xffffffffu, v);
-            if (p >= 0 && (grp >> lane) == 1u) c.occ[v * kV4Words + warp] = grp;
-            if (tid < 4) { const int p2 = lo + kV4W + tid - 3; atomicOr(&c.occ[v4_rb8(c.rbw, (uint32_t) p2) * kV4Words + (kV4W >> 5)], 1u << tid); }
+            if (p >= 0 && (grp >> lane) == 1u) { c.occ[v * kV4Words + warp] = grp; atomicAdd(&c.pcnt[v], (uint32_t) __popc(grp)); atomicOr(&c.occw[v], 1u << warp); }
+            if (tid < 2) { const int p2 = lo + kV4N + tid - 3; const uint32_t v2 = v4_rb8(c.rbw, (uint32_t) p2); atomicOr(&c.occ[v2 * kV4Words + (kV4N >> 5)], 1u << tid); atomicAdd(&c.pcnt[v2], 1u); }
         }
         v4_spec_position(c, lo, tid);                                    // chain records against G (global-memory latency lives here)
-        if (tid < 2) v4_spec_position(c, lo, kV4W + tid);
+        V4_TICK(1);
         {   // link builder: nearest earlier position of the window in the same bucket.  Groups of 4 warps own a bucket table;
             // inside a group the warps take turns in position order, then positions without a predecessor in their own
             // group look at the final tables of the groups before theirs.
@@ -914,6 +976,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory");
             }
             __syncthreads();
+            V4_TICK(2);
             if (valid && dist == 0) {
                 for (int g2 = g - 1; g2 >= 0; g2--) {
                     const uint32_t prev = gtab[g2 * kV4Buckets + bk];
@@ -921,42 +984,22 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 }
             }
             c.blink[tid] = (uint16_t) dist;
-            if (tid == 0) {                                              // the two look-ahead positions
-                for (int rel = kV4W; rel < kV4N; rel++) {
-                    const uint32_t k2 = c.key[rel];
-                    uint32_t d2 = 0;
-                    if (!(k2 & kV4KeyInvalid)) {
-                        const uint32_t b2 = v4_bucket_of(k2);
-                        if (rel == kV4W + 1 && !(c.key[kV4W] & kV4KeyInvalid) && v4_bucket_of(c.key[kV4W]) == b2) d2 = 1;
-                        for (int g2 = kV4Groups - 1; g2 >= 0 && !d2; g2--) {
-                            const uint32_t prev = gtab[g2 * kV4Buckets + b2];
-                            if (prev) d2 = (uint32_t) rel - (prev - 1u);
-                        }
-                    }
-                    c.blink[rel] = (uint16_t) d2;
-                }
-            }
-            if (tid >= 256 && tid < 512) {                               // pcnt[ctx]: window positions with that context byte
-                uint32_t n = 0;
-                for (int wq = 0; wq < kV4Words - 1; wq++) n += (uint32_t) __popc(v4_ctxbits(c, (uint32_t) (tid - 256), wq));
-                c.pcnt[tid - 256] = (uint16_t) n;
-            }
         }
         __syncthreads();
+        V4_TICK(3);
         v4_link_position(c, tid);
-        if (tid < 2) v4_link_position(c, kV4W + tid);
         __syncthreads();
+        V4_TICK(4);
         const int wlevel = s_run.level;
-        v4_frozen_position(c, lo, tid, wlevel);
+        if (tid < kV4W) v4_frozen_position(c, lo, tid, wlevel);
         if (tid == 0) {
             V4Win w; w.lo = lo; w.wend = wend; w.entry = s_run.ip; w.level = wlevel; w.rpos = -1; w.level2 = wlevel;
             w.skip_push = s_run.skip_push; w.prev_lit = s_run.prev_lit;
             s_win = w;
         }
-        { const uint32_t fl = c.fdec[tid] & 511u; c.dec[tid] = fl ? (fl | (kV4Match << 9)) : (kV4Lit << 9); }
-        if (tid < 2) { c.dec[kV4W + tid] = kV4Lit << 9; c.mark[kV4W + tid] = 0; c.plit[kV4W + tid] = 0; }
-        if (tid < 2) c.mbits[(kV4W >> 5) + tid] = 0;
+        { const uint32_t fl = tid < kV4W ? c.fdec[tid] & 511u : 0u; c.dec[tid] = fl ? (fl | (kV4Match << 9)) : (kV4Lit << 9); }
         __syncthreads();
+        V4_TICK(5);
         const long long t1 = clock64();
         cyc_spec += t1 - t0;
         // ================================================= ROUNDS ===============================================
@@ -975,6 +1018,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             for (int l = 0; l < 5; l++) { const int nx = __shfl_sync(0xffffffffu, cj[l], cj[l] & 31); cj[l + 1] = cj[l] < segend ? nx : cj[l]; }
             E[tid] = (uint16_t) cj[5];
             c.plit[tid] = 0;
+            if (tid < 256) c.mcnt[tid] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
             __syncthreads();
             int cur = entry_rel;
@@ -989,6 +1033,11 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             marked = (M >> lane) & 1u;
             c.mark[tid] = (uint8_t) marked;
             if (lane == 0) c.mbits[warp] = M;
+            {   // mcnt[ctx] = marked positions per context (bounds the inserts a record can have missed)
+                const uint32_t cv = marked ? v4_ctx_of(c.key[tid]) : 256u + (uint32_t) lane;
+                const uint32_t grp = __match_any_sync(0xffffffffu, cv);
+                if (marked && (grp >> lane) == 1u) atomicAdd(&c.mcnt[cv], (uint32_t) __popc(grp));
+            }
             if (marked) {
                 const int t = tid + (int) v4_dec_step(mydec);
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
@@ -1025,14 +1074,26 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             // ---- every position re-derives its decision
             const V4Win w = s_win;
             uint32_t nd = mydec;
-            if (tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid);
+#if defined(ZL_V4_PROFILE)
+            uint32_t prof[3] = { 0, 0, 0 };
+            if (tid < 3) s_dmax[tid] = 0;
+            __syncthreads();
+            if (marked && tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid, prof);
+            atomicMax(&s_dmax[0], prof[0]); atomicMax(&s_dmax[1], prof[1]); atomicMax(&s_dmax[2], prof[2]);
+#else
+            if (marked && tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid);      // unmarked positions keep their (frozen) decision
+#endif
             const int changed = __syncthreads_or(marked && ((nd ^ mydec) & kV4DecCmp) != 0);
+#if defined(ZL_V4_PROFILE)
+            if (tid == 0) { s_ph[13] += s_dmax[0]; s_ph[14] += s_dmax[1]; s_ph[15] += s_dmax[2]; }
+#endif
             c.dec[tid] = nd;
             const long long r3 = clock64();
             cyc_orbit += r1 - r0; cyc_rank += r2 - r1; cyc_decide += r3 - r2;
             if (!changed) break;
         }
         const long long t2 = clock64();
+        tprev = t2;
         cyc_rounds += t2 - t1;
         n_windows++;
         // ================================================= FINALIZE =============================================
@@ -1043,6 +1104,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
             c.sup[tid] = 0;
             __syncthreads();
+            V4_TICK(6);
             const uint32_t kx = c.key[tid];
             const bool valid = !(kx & kV4KeyInvalid);
             const uint32_t ctx = v4_ctx_of(kx);
@@ -1062,6 +1124,12 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             for (int o = 16; o > 0; o >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, o); sya += __shfl_xor_sync(0xffffffffu, sya, o); }
             if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); s_wsym[warp] = (int) sy; s_wsya[warp] = (int) sya; }
             __syncthreads();
+            V4_TICK(7);
+#if defined(ZL_V4_PROFILE)
+            if (tid < 4) s_dmax[tid] = 0;
+            __syncthreads();
+            const uint32_t q0 = (uint32_t) clock64();
+#endif
             if (tid < 256) {
                 uint32_t run = 0;
                 #pragma unroll 8
@@ -1069,14 +1137,23 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 wcnt[32 * 256 + tid] = (uint16_t) run;
             } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
             else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
-            else if (tid >= 512 && tid < 768) c.mru2[tid - 512] = v4_mru_state(c, w, Wn - 1, (uint32_t) (tid - 512));
+            if (warp >= 10) {                                             // carried word MRU: 22 warps share the 256 contexts
+                for (int cq = warp - 10; cq < 256; cq += 22) { const uint32_t v = v4_mru_carry_warp(c, w, Wn, (uint32_t) cq, lane); if (lane == 0) c.mru2[cq] = v; }
+            }
+#if defined(ZL_V4_PROFILE)
+            atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);
             __syncthreads();
+            if (tid == 0) { s_ph[16] += s_dmax[0]; s_ph[17] += s_dmax[1]; s_ph[18] += s_dmax[2]; }
+#endif
+            __syncthreads();
+            V4_TICK(8);
             c.rank[tid] = valid ? (uint16_t) (wcnt[warp * 256 + ctx] + inwarp) : (uint16_t) 0;
-            if (tid < 2) { const uint32_t k2 = c.key[kV4W + tid]; c.rank[kV4W + tid] = (k2 & kV4KeyInvalid) ? (uint16_t) 0 : wcnt[32 * 256 + v4_ctx_of(k2)]; }
             __syncthreads();
+            V4_TICK(9);
             uint32_t suffix = 0;
             if (marked) suffix = v4_claim_slot(c, tid);
             __syncthreads();
+            V4_TICK(10);
             if (marked) {
                 v4_apply_position(c, lo, tid, suffix);
                 const int ti = s_nt + s_wtok[warp] + __popc(bt & v4_lt_mask(lane));
@@ -1085,6 +1162,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (w.rpos >= 0 && lo + tid == w.rpos) s_rpos_nt = ti;
             }
             __syncthreads();
+            V4_TICK(11);
             if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += wcnt[32 * 256 + tid]; }
             if (tid == 0) {
                 V4Run r = s_run;
@@ -1100,6 +1178,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             }
         }
         __syncthreads();
+        V4_TICK(12);
         cyc_final += clock64() - t2;
     }
     if (tid == 0) {
@@ -1120,6 +1199,7 @@ __global__ void __launch_bounds__(kV4W, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             atomicAdd(&counters->cyc_rank, (unsigned long long) cyc_rank);
             atomicAdd(&counters->cyc_decide, (unsigned long long) cyc_decide);
             atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));
+            for (int i = 0; i < 24; i++) atomicAdd(&counters->ph[i], s_ph[i]);
         }
     }
 }

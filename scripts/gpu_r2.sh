@@ -10,9 +10,9 @@ if [ "$2" != "notests" ]; then
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
   tail -15 gpurun_out/${TAG}_pytest.log
 fi
-timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
-cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
+ZLB_V4_TRACE=1 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json; grep "v4 phases" gpurun_out/${TAG}_bench.err | tail -2; tail -3 gpurun_out/${TAG}_bench.err
 if [ "$3" == "e4" ]; then
-  timeout 600 python bench.py --steps 2 --warmup 3 --level 4 --no-decode > gpurun_out/${TAG}_bench_e4.json 2> gpurun_out/${TAG}_bench_e4.err; echo "bench e4 rc=$?"
-  cat gpurun_out/${TAG}_bench_e4.json | cut -c1-2500; tail -3 gpurun_out/${TAG}_bench_e4.err
+  ZLB_V4_TRACE=1 timeout 600 python bench.py --steps 2 --warmup 3 --level 4 --no-decode > gpurun_out/${TAG}_bench_e4.json 2> gpurun_out/${TAG}_bench_e4.err; echo "bench e4 rc=$?"
+  cat gpurun_out/${TAG}_bench_e4.json | cut -c1-2500; grep "v4 phases" gpurun_out/${TAG}_bench_e4.err | tail -1; tail -3 gpurun_out/${TAG}_bench_e4.err
 fi

@@ -69,6 +69,9 @@ int main(int argc, char** argv) {
     int staged_hi = -16;
     unsigned long long st_rounds = 0, st_windows = 0, st_general = 0, st_decides = 0, st_maxrounds = 0, st_hist[9] = {0};
     std::vector<uint32_t> cntw(256);
+    // the kernel re-derives the decisions of the MARKED positions only (unmarked ones keep their frozen decision until the
+    // orbit reaches them); ZL_V4_ALL=1 evaluates every position each round (fewer rounds, 4x the work)
+    const bool marked_only = !(getenv("ZL_V4_ALL") && atoi(getenv("ZL_V4_ALL")) != 0);
 
     for (int k = 0; k < nwin; k++) {
         const int lo = k * kV4W;
@@ -80,13 +83,17 @@ int main(int argc, char** argv) {
         // ---- SPEC
         for (int rel = 0; rel < kV4N; rel++) c.key[rel] = v4_key_of(c, lo + rel);
         memset(c.occ, 0, sizeof(uint32_t) * 256 * kV4Words);
-        for (int i = 0; i < kV4W + 4; i++) {                               // bit i of occ[b]: in[lo + i - 3] == b
+        for (int i = 0; i < kV4N + 2; i++) {                               // bit i of occ[b]: in[lo + i - 3] == b
             const int p = lo + i - 3;
             if (p < 0) continue;
             const uint32_t b = v4_rb8(c.rbw, (uint32_t) p);
             c.occ[b * kV4Words + (i >> 5)] |= 1u << (i & 31);
         }
-        for (int cq = 0; cq < 256; cq++) { uint32_t n = 0; for (int wq = 0; wq < kV4Words - 1; wq++) n += (uint32_t) z4_popc(v4_ctxbits(c, (uint32_t) cq, wq)); c.pcnt[cq] = (uint16_t) n; }
+        for (int cq = 0; cq < 256; cq++) {
+            uint32_t n = 0, ow = 0;
+            for (int wq = 0; wq < kV4Words; wq++) { n += (uint32_t) z4_popc(c.occ[cq * kV4Words + wq]); if (wq < 32 && c.occ[cq * kV4Words + wq]) ow |= 1u << wq; }
+            c.pcnt[cq] = n; c.occw[cq] = ow;
+        }
         v4_bucket_pass_serial(c);
         for (int rel = 0; rel < kV4N; rel++) v4_link_position(c, rel);
         for (int rel = 0; rel < kV4N; rel++) v4_spec_position(c, lo, rel);
@@ -120,8 +127,10 @@ int main(int argc, char** argv) {
                 c.rank[rel] = (uint16_t) cntw[v4_ctx_of(kx)];
                 if (c.mark[rel]) cntw[v4_ctx_of(kx)]++;
             }
+            for (int i = 0; i < 256; i++) c.mcnt[i] = cntw[i];
             bool changed = false;
             for (int rel = w.entry - lo; rel < wend - lo; rel++) {
+                if (marked_only && !c.mark[rel]) { c.ndec[rel] = c.dec[rel]; continue; }
                 const uint32_t nd = v4_decide(c, w, rel);
                 st_decides++;
                 c.ndec[rel] = nd;
