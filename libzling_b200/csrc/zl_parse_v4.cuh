@@ -54,8 +54,22 @@ ZL_HD uint32_t v4_dec_ref(uint32_t d)  { return (d >> 12) & 0x1fffu; }
 ZL_HD uint32_t v4_dec_step(uint32_t d) { const uint32_t k = v4_dec_kind(d); return k == kV4Match ? v4_dec_len(d) : (k == kV4Lit ? 1u : 2u); }
 ZL_HD uint32_t v4_dec_syms(uint32_t d) { return v4_dec_kind(d) == kV4Match ? 2u : 1u; }
 // fx word: frozen slot head (16) | flags << 16
-constexpr uint32_t kV4F_SELF = 1u << 16, kV4F_L1 = 1u << 17, kV4F_L2 = 1u << 18;
+constexpr uint32_t kV4F_SELF = 1u << 16, kV4F_L1 = 1u << 17, kV4F_L2 = 1u << 18, kV4F_ST = 1u << 19;   // ST: a slot read by the records of x / x+1 / x+2 may be overwritten inside the window
 
+// host-side statistics of the replay (tests/cxx/parse_v4_sim.cu with -DZL_V4_STATS): loop trip counts of the serial helpers
+#if defined(ZL_V4_STATS)
+struct V4Stats { unsigned long long calls[8], steps[8], maxsteps[8], hist[8][16]; };
+static V4Stats g_v4stats;
+static inline void v4_stat(int k, unsigned long long n) {
+    g_v4stats.calls[k]++; g_v4stats.steps[k] += n; if (n > g_v4stats.maxsteps[k]) g_v4stats.maxsteps[k] = n;
+    int b = 0; while ((1ull << b) <= n && b < 15) b++; g_v4stats.hist[k][b]++;
+}
+#endif
+#if defined(ZL_V4_STATS) && !defined(__CUDA_ARCH__)
+#define V4_STAT(k, n) v4_stat(k, (unsigned long long) (n))
+#else
+#define V4_STAT(k, n) do { } while (0)
+#endif
 // ---- portable intrinsics ---------------------------------------------------------------------------------------------
 ZL_HD uint32_t z4_funnel(uint32_t lo, uint32_t hi, uint32_t sh) {
 #if defined(__CUDA_ARCH__)
@@ -396,6 +410,17 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
         if (c.link[rel + 1]) fl |= kV4F_L1;
         if (c.link[rel + 2]) fl |= kV4F_L2;
     }
+    // static bound of the staleness tests (v4_maybe_stale without the per-round marked counts): positions with the context byte
+    {
+        bool st = nvis > 0 && (hdr >> 5) + 1u <= c.pcnt[v4_ctx_of(c.key[rel])];
+        if (lazy_matters) {
+            for (int q = 1; q <= 2; q++) {
+                const uint32_t hq = c.hdr[rel + q];
+                if ((hq & 31u) && (hq >> 5) + 1u <= c.pcnt[v4_ctx_of(c.key[rel + q])] + 1u) st = true;
+            }
+        }
+        if (st) fl |= kV4F_ST;
+    }
     c.fdec[rel] = flen | (fbest << 9) | (fslot << 18);
     c.fx[rel] = (c.fx[rel] & 0xffffu) | fl;
 }
@@ -412,6 +437,7 @@ ZL_HD uint32_t v4_ctxbits(const V4Ctx& c, uint32_t cq, int w) {
 // inserts into context cq pending before rel: marked positions y < rel with that context.  Exact, on demand (the
 // per-context ranks of ALL positions are only built once per window, after the rounds: v4_head_final)
 ZL_HD uint32_t v4_rank_live(const V4Ctx& c, int rel, uint32_t cq) {
+    V4_STAT(1, rel >> 5);
     uint32_t n = 0;
     const int wl = rel >> 5;
     for (int w = 0; w < wl; w++) n += (uint32_t) z4_popc(v4_ctxbits(c, cq, w) & c.mbits[w]);
@@ -433,13 +459,15 @@ ZL_HD uint32_t v4_cnt_lazy(const V4Ctx& c, int rel, int q) {
 // is some same-key position before z, not after xrel, pending?
 ZL_HD bool v4_link_hazard(const V4Ctx& c, int z, int xrel, bool self_counts) {
     int y = z;
+    int steps = 0;
     while (true) {
         const uint32_t d = c.link[y];
-        if (!d) return false;
+        if (!d) { V4_STAT(0, steps); return false; }
         y -= (int) d;
+        steps++;
         if (y > xrel) continue;
-        if (y == xrel) { if (self_counts) return true; continue; }
-        if (c.mark[y]) return true;
+        if (y == xrel) { if (self_counts) { V4_STAT(0, steps); return true; } continue; }
+        if (c.mark[y]) { V4_STAT(0, steps); return true; }
     }
 }
 // Leading nodes of a record whose ring slots have not been overwritten after `kc` further inserts into the context.
@@ -580,6 +608,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
     const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
     const uint32_t kx = c.key[rel];
     const uint32_t chk = kx >> 21, cq = v4_ctx_of(kx);
+    V4_STAT(4, 1);
     int best = kMinLen - 1, visited = 0, first_pending = -1;
     uint32_t ref = 0;
     bool done = false;
@@ -614,6 +643,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
     }
     if (!done && visited < D && (nvis > 0 || stale0)) {
         if (stale0) {                                                    // the record's first slot has been overwritten: replay literally
+            V4_STAT(5, 1);
             const uint32_t head = (c.cnt[cq] + kc0) & (kRing - 1);
             const uint32_t suffix = first_pending >= 0 ? v4_head_live(c, first_pending) : (c.fx[rel] & 0xffffu);
             uint32_t bn = 0;
@@ -686,31 +716,46 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
     const int whi = xrel >> 5, wlo = elo >> 5;
     // words of the window that hold a byte cq at all (occw), between the first possible push and xrel, newest first
     uint32_t words = c.occw[cq] & (0xffffffffu >> (31 - whi)) & (0xffffffffu << wlo);
+    int st_words = 0, st_push = 0;
+    (void) st_words; (void) st_push;
     while (words) {
+        st_words++;
         const int wi = 31 - z4_clz(words);
         words &= ~(1u << wi);
         uint32_t m = occ[wi] & c.mbits[wi];
         if (wi == whi) m &= 0xffffffffu >> (31 - (xrel & 31));
         if (wi == wlo) m &= 0xffffffffu << (elo & 31);
         while (m) {
+            st_push++;
             const int b = 31 - z4_clz(m);
             m &= ~(1u << b);
             const int e = wi * 32 + b;
             const uint32_t xe = (uint32_t) (w.lo + e);
             const uint32_t pw = (v4_rb8(c.rbw, xe - 2) << 8) | v4_rb8(c.rbw, xe - 1);
             if (have) {                                                  // pw is the front before the pending push a
-                if (u || pw != a) return a | (pw << 16);
+                if (u || pw != a) { V4_STAT(2, st_words); V4_STAT(3, st_push); return a | (pw << 16); }
                 // the pending push was a no-op: the state is that after this (older) push
             }
             have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
         }
     }
+    V4_STAT(2, st_words); V4_STAT(3, st_push);
     if (!have) return base;
     if (u || (base & 0xffffu) != a) return a | (base << 16);
     return base;
 }
 
 // ---- ROUNDS: the decision of a position given the marks --------------------------------------------------------------------
+// the pieces of v4_decide the kernel runs as separate, queue-fed stages (same results: the static flags of fx are a superset
+// of the conditions under which v4_hazard can say yes)
+ZL_HD uint32_t v4_dec_match(uint32_t len, uint32_t ref) { return len | (kV4Match << 9) | (ref << 12); }
+ZL_HD uint32_t v4_decide_word(const V4Ctx& c, const V4Win& w, int rel) {   // no match is taken at rel: word-MRU test, lz.cpp:172-185
+    const int x = w.lo + rel;
+    const uint32_t m = v4_mru_state(c, w, rel, v4_ctx_of(c.key[rel]));
+    const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
+    const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
+    return kind << 9;
+}
 #if defined(ZL_V4_PROFILE) && defined(__CUDA_ARCH__)
 #define V4_PROF_T() ((uint32_t) clock64())
 #else
@@ -888,6 +933,8 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
     __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
     __shared__ uint32_t s_dmax[4];
+    __shared__ uint32_t s_pflag[8];                                              // FINALIZE: contexts that received a word-MRU push in the window
+    __shared__ int s_nq[4];                                                      // queue lengths of the decide stages
     __shared__ unsigned long long s_ph[24];                                      // phase timers (thread 0's clock between barriers)
     long long tprev = 0;
 #define V4_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); s_ph[i] += (unsigned long long) (now_ - tprev); tprev = now_; } } while (0)
@@ -905,6 +952,9 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
     uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
     uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + 4096);                   // FINALIZE: [33][256] marked positions per (warp, context)
+    uint16_t* qhaz = reinterpret_cast<uint16_t*>(scratch + 24576);                  // ROUNDS: positions waiting for the hazard check,
+    uint16_t* qgen = qhaz + kV4T;                                                   //         for the full probe on the pending view,
+    uint16_t* qmru = qgen + kV4T;                                                   //         for the word-MRU test
 
     for (int i = tid; i < 256; i += kV4T) { c.cnt[i] = 0; c.mru[i] = 0; }
     long long cyc_spec = 0, cyc_rounds = 0, cyc_final = 0, cyc_orbit = 0, cyc_rank = 0, cyc_decide = 0;
@@ -1020,6 +1070,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             c.plit[tid] = 0;
             if (tid < 256) c.mcnt[tid] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
+            if (tid < 3) s_nq[tid] = 0;
             __syncthreads();
             int cur = entry_rel;
             while ((cur >> 5) < warp && cur < Wn) cur = E[cur];
@@ -1071,22 +1122,43 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             }
             __syncthreads();
             const long long r2 = clock64();
-            // ---- every position re-derives its decision
+            // ---- every MARKED position re-derives its decision (unmarked ones keep their frozen decision until the orbit reaches
+            // them).  The work is staged through queues so that each piece of code runs on a dense set of positions, one
+            // position per warp first (the stages are bound by instruction issue: a warp pays for a path as soon as one of
+            // its lanes takes it): A classify -> B hazard checks -> C full probes on the pending view -> D word-MRU tests
             const V4Win w = s_win;
             uint32_t nd = mydec;
-#if defined(ZL_V4_PROFILE)
-            uint32_t prof[3] = { 0, 0, 0 };
-            if (tid < 3) s_dmax[tid] = 0;
+            const int level_here = (w.rpos >= 0 && lo + tid >= w.rpos) ? w.level2 : w.level;
+            if (marked && tid >= entry_rel && tid < Wn) {
+                const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
+                if (level_here != w.level) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) tid;
+                else if (fxw >> 16) qhaz[atomicAdd(&s_nq[0], 1)] = (uint16_t) tid;
+                else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
+                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) tid;
+            }
+            c.ndec[tid] = nd;
             __syncthreads();
-            if (marked && tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid, prof);
-            atomicMax(&s_dmax[0], prof[0]); atomicMax(&s_dmax[1], prof[1]); atomicMax(&s_dmax[2], prof[2]);
-#else
-            if (marked && tid >= entry_rel && tid < Wn) nd = v4_decide(c, w, tid);      // unmarked positions keep their (frozen) decision
-#endif
+            const int qslot = lane * 32 + warp;                          // queue entry of this thread: entries 0..31 go to 32 different warps
+            if (qslot < s_nq[0]) {
+                const int rel = qhaz[qslot];
+                const uint32_t fd = c.fdec[rel];
+                if (v4_hazard(c, rel, fd, c.fx[rel], depth_lazy2(w.level))) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) rel;
+                else if (fd & 511u) c.ndec[rel] = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
+                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+            }
+            __syncthreads();
+            if (qslot < s_nq[1]) {
+                const int rel = qgen[qslot];
+                uint32_t rf = 0;
+                const uint32_t len = (uint32_t) v4_probe_general(c, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
+                if (len) c.ndec[rel] = v4_dec_match(len, rf);
+                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+            }
+            __syncthreads();
+            if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
+            __syncthreads();
+            nd = c.ndec[tid];
             const int changed = __syncthreads_or(marked && ((nd ^ mydec) & kV4DecCmp) != 0);
-#if defined(ZL_V4_PROFILE)
-            if (tid == 0) { s_ph[13] += s_dmax[0]; s_ph[14] += s_dmax[1]; s_ph[15] += s_dmax[2]; }
-#endif
             c.dec[tid] = nd;
             const long long r3 = clock64();
             cyc_orbit += r1 - r0; cyc_rank += r2 - r1; cyc_decide += r3 - r2;
@@ -1103,8 +1175,10 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             // per-context ranks of the marked positions -> ring slots of the pending inserts
             reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
             c.sup[tid] = 0;
+            if (tid < 8) s_pflag[tid] = 0;
             __syncthreads();
             V4_TICK(6);
+            if (marked) { const uint32_t c3 = v4_rb8(c.rbw, (uint32_t) (lo + tid) - 3u); atomicOr(&s_pflag[c3 >> 5], 1u << (c3 & 31)); }   // contexts that received a push
             const uint32_t kx = c.key[tid];
             const bool valid = !(kx & kV4KeyInvalid);
             const uint32_t ctx = v4_ctx_of(kx);
@@ -1138,7 +1212,12 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
             else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
             if (warp >= 10) {                                             // carried word MRU: 22 warps share the 256 contexts
-                for (int cq = warp - 10; cq < 256; cq += 22) { const uint32_t v = v4_mru_carry_warp(c, w, Wn, (uint32_t) cq, lane); if (lane == 0) c.mru2[cq] = v; }
+                for (int cq = warp - 10; cq < 256; cq += 22) {
+                    uint32_t v;
+                    if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_carry_warp(c, w, Wn, (uint32_t) cq, lane);
+                    else v = w.rpos >= 0 ? 0u : c.mru[cq];               // no push in this window: the carried state (zeroed by a roll-over)
+                    if (lane == 0) c.mru2[cq] = v;
+                }
             }
 #if defined(ZL_V4_PROFILE)
             atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);
