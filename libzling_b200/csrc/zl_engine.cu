@@ -173,7 +173,11 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaMalloc(&c->d_ctxoff, nb * 257 * sizeof(uint32_t)));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3_layout(depth_main(4), depth_lazy1(4)).total));
-    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(depth_main(4), depth_lazy1(4)).total));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(2, 1).total));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(4, 1).total));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(8, 3).total));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(16, 4).total));
     { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv >= '1' && *pv <= '4') c->parse_version = *pv - '0'; }
     { const char* pv = getenv("ZLB_V3_SERIAL"); if (pv && *pv == '1') c->v3_serialize = 1; }
     { const char* pv = getenv("ZLB_MTF"); if (pv && *pv >= '1' && *pv <= '2') c->mtf_version = *pv - '0'; }
@@ -299,7 +303,13 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V4Layout lay = v4_layout(dmax, lmax);
             if (pass == 0) CU(cudaMemsetAsync(c->d_v4c, 0, sizeof(V4Counters), st));
-            zl_rolz_parse_v4_kernel<<<nb, kV4T, lay.total, st>>>(pa, dmax, lmax, e->level, c->d_v4c);
+            switch (e->level) {                                  // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
+                case 0:  zl_rolz_parse_v4_kernel<2, 1><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+                case 1:  zl_rolz_parse_v4_kernel<4, 1><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+                case 2:  zl_rolz_parse_v4_kernel<6, 2><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+                case 3:  zl_rolz_parse_v4_kernel<8, 3><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+                default: zl_rolz_parse_v4_kernel<16, 4><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+            }
         } else if (c->parse_version == 3) {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V3Layout lay = v3_layout(dmax, lmax);

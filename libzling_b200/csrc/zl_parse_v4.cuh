@@ -39,6 +39,7 @@ constexpr int kV4R       = 2048;                // byte ring: >= 4 + kV4N + 264 
 constexpr int kV4Tail    = 288;                 // bytes staged past the last look-ahead position
 constexpr int kV4Buckets = 4096;                // buckets of the link builder
 constexpr int kV4Words   = (kV4N + 2 + 31) / 32 + 1;  // bitset words over window positions (+2: contexts of the last positions; +1 word: funnel reads)
+constexpr int kV4PfWords = 128;                 // 4096-bit Bloom bitmap of the pushed (context, word) pairs
 constexpr uint32_t kV4KeyInvalid = 0x80000000u; // position cannot be probed (first two bytes / last 273 bytes of the block)
 constexpr uint32_t kV4KeyMask    = 0x1fffffu;   // (context << 13) | hash slot
 constexpr uint32_t kV4Auto       = 0xffu;       // plan entry: predict the level (see v4_next_level)
@@ -138,7 +139,7 @@ ZL_HD uint32_t z4_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------------
 struct V4Layout {
     int dmax, lmax;
-    int rb, key, link, blink, pcnt, occw, mcnt, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
+    int rb, key, link, blink, pcnt, occw, mcnt, pf, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
     int scratch_bytes;
 };
 // scratch is a union: SPEC uses it for the link builder's bucket tables, the rounds for the orbit / rank tables
@@ -156,6 +157,7 @@ __host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
     L.pcnt  = take(4 * 256);
     L.occw  = take(4 * 256);
     L.mcnt  = take(4 * 256);
+    L.pf    = take(4 * kV4PfWords);
     L.hdr   = take(4 * kV4N);
     L.node  = take(4 * kV4N * dmax);
     L.nodeq = take(4 * kV4N * lmax);
@@ -185,13 +187,15 @@ struct V4Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory (indexed by rel = x - lo unless noted)
     uint32_t* rbw;                              // input bytes: ring of kV4R bytes viewed as words, indexed by block position
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* pcnt; uint32_t* occw; uint32_t* mcnt; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* pcnt; uint32_t* occw; uint32_t* mcnt; uint32_t* pf; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
     uint32_t* fdec; uint32_t* fx; uint16_t* rank; uint8_t* mark; uint8_t* plit; uint8_t* sup; uint32_t* dec; uint32_t* ndec;
     uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c;
                                                 // position lo + i - 2 has context c)
     // pcnt[c] = bytes of value c among in[lo - 3 .. lo + N - 2] (the set bits of occ[c]): an upper bound of the window positions
     // whose context byte is c, i.e. of the inserts this window can make into context c
     // occw[c]: bit w set <=> word w of occ[c] is not empty (w < 32);  mcnt[c] = MARKED positions whose context byte is c (per round)
+    // pf: Bloom bitmap (per round) of the (context, word) pairs pushed by the marked positions: a word test whose pair is neither
+    //     in it nor in the carried MRU entry cannot hit (v4_decide_word), which spares the scan of the pushes
     uint32_t* mbits;                            // [kV4Words]: bit i <=> position lo + i is a token start
     uint32_t* cnt; uint32_t* mru; uint32_t* mru2;   // carried: inserts per context before the window, word MRU at the window's entry
     uint32_t* last;                             // host replay only: bucket table of the serial link builder
@@ -199,7 +203,7 @@ struct V4Ctx {
 };
 __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint32_t*) (smem + L.pcnt); c.occw = (uint32_t*) (smem + L.occw); c.mcnt = (uint32_t*) (smem + L.mcnt); c.hdr = (uint32_t*) (smem + L.hdr);
+    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint32_t*) (smem + L.pcnt); c.occw = (uint32_t*) (smem + L.occw); c.mcnt = (uint32_t*) (smem + L.mcnt); c.pf = (uint32_t*) (smem + L.pf); c.hdr = (uint32_t*) (smem + L.hdr);
     c.node = (uint32_t*) (smem + L.node); c.nodeq = (uint32_t*) (smem + L.nodeq); c.fdec = (uint32_t*) (smem + L.fdec);
     c.fx = (uint32_t*) (smem + L.fx); c.rank = (uint16_t*) (smem + L.rank); c.mark = smem + L.mark; c.plit = smem + L.plit;
     c.sup = smem + L.sup; c.dec = (uint32_t*) (smem + L.dec); c.ndec = (uint32_t*) (smem + L.ndec);
@@ -749,10 +753,22 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
 // the pieces of v4_decide the kernel runs as separate, queue-fed stages (same results: the static flags of fx are a superset
 // of the conditions under which v4_hazard can say yes)
 ZL_HD uint32_t v4_dec_match(uint32_t len, uint32_t ref) { return len | (kV4Match << 9) | (ref << 12); }
+ZL_HD uint32_t v4_pf_hash(uint32_t ctx, uint32_t word) { return (((ctx << 16) | word) * 2654435761u) >> 20; }   // 12 bits
+// the push a token END at position xe makes: context in[xe-3], word in[xe-2..xe-1]
+ZL_HD void v4_push_of(const V4Ctx& c, uint32_t xe, uint32_t* ctx3, uint32_t* word) {
+    const uint32_t t = v4_rb32(c.rbw, xe - 3u);
+    *ctx3 = t & 0xffu; *word = ((t >> 8) & 0xffu) << 8 | ((t >> 16) & 0xffu);
+}
 ZL_HD uint32_t v4_decide_word(const V4Ctx& c, const V4Win& w, int rel) {   // no match is taken at rel: word-MRU test, lz.cpp:172-185
     const int x = w.lo + rel;
-    const uint32_t m = v4_mru_state(c, w, rel, v4_ctx_of(c.key[rel]));
+    const uint32_t cq = v4_ctx_of(c.key[rel]);
     const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
+    {   // quick reject: every MRU entry is a word pushed in this window or a carried one (zero after a roll-over)
+        const uint32_t base = (w.rpos >= 0 && x >= w.rpos) ? 0u : c.mru[cq];
+        const uint32_t h = v4_pf_hash(cq, wd);
+        if (!((c.pf[h >> 5] >> (h & 31u)) & 1u) && (base & 0xffffu) != wd && (base >> 16) != wd) return kV4Lit << 9;
+    }
+    const uint32_t m = v4_mru_state(c, w, rel, cq);
     const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
     return kind << 9;
 }
@@ -924,7 +940,11 @@ __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
 }
 
 // ---- the kernel: grid = blocks of the batch, kV4T threads, thread t owns position lo + t of the current window -----------
-__global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int dmax, int lmax, int base_level, V4Counters* counters) {
+// DMAX / LMAX (chain nodes recorded per position / of them with a stored candidate position) are compile-time: every
+// shared-memory offset is then a constant
+template <int DMAX, int LMAX>
+__global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int base_level, V4Counters* counters) {
+    constexpr int dmax = DMAX, lmax = LMAX;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1069,6 +1089,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             E[tid] = (uint16_t) cj[5];
             c.plit[tid] = 0;
             if (tid < 256) c.mcnt[tid] = 0;
+            if (tid >= 256 && tid < 256 + kV4PfWords) c.pf[tid - 256] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
             if (tid < 3) s_nq[tid] = 0;
             __syncthreads();
@@ -1090,6 +1111,10 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (marked && (grp >> lane) == 1u) atomicAdd(&c.mcnt[cv], (uint32_t) __popc(grp));
             }
             if (marked) {
+                uint32_t c3, pw;
+                v4_push_of(c, (uint32_t) (lo + tid), &c3, &pw);
+                const uint32_t h = v4_pf_hash(c3, pw);
+                atomicOr(&c.pf[h >> 5], 1u << (h & 31u));
                 const int t = tid + (int) v4_dec_step(mydec);
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
                 else { s_exit = lo + t; s_lastrel = tid; }
@@ -1129,15 +1154,30 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             const V4Win w = s_win;
             uint32_t nd = mydec;
             const int level_here = (w.rpos >= 0 && lo + tid >= w.rpos) ? w.level2 : w.level;
-            if (marked && tid >= entry_rel && tid < Wn) {
-                const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
-                if (level_here != w.level) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) tid;
-                else if (fxw >> 16) qhaz[atomicAdd(&s_nq[0], 1)] = (uint16_t) tid;
-                else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
-                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) tid;
+            {
+                int which = -1;                                          // queue this position goes to: 0 hazard check, 1 full probe, 2 word test
+                if (marked && tid >= entry_rel && tid < Wn) {
+                    const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
+                    if (level_here != w.level) which = 1;
+                    else if (fxw >> 16) which = 0;
+                    else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
+                    else which = 2;
+                }
+                #pragma unroll
+                for (int qi = 0; qi < 3; qi++) {                         // one shared-memory atomic per warp and queue
+                    const uint32_t bal = __ballot_sync(0xffffffffu, which == qi);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_nq[qi], __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                        if (which == qi) (qi == 0 ? qhaz : qi == 1 ? qgen : qmru)[base + __popc(bal & v4_lt_mask(lane))] = (uint16_t) tid;
+                    }
+                }
             }
             c.ndec[tid] = nd;
+            tprev = r2;
             __syncthreads();
+            V4_TICK(13);
             const int qslot = lane * 32 + warp;                          // queue entry of this thread: entries 0..31 go to 32 different warps
             if (qslot < s_nq[0]) {
                 const int rel = qhaz[qslot];
@@ -1147,6 +1187,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
             }
             __syncthreads();
+            V4_TICK(14);
             if (qslot < s_nq[1]) {
                 const int rel = qgen[qslot];
                 uint32_t rf = 0;
@@ -1155,8 +1196,11 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
             }
             __syncthreads();
+            V4_TICK(15);
+            if (tid == 0) { s_ph[20] += (unsigned long long) s_nq[0]; s_ph[21] += (unsigned long long) s_nq[1]; s_ph[22] += (unsigned long long) s_nq[2]; }
             if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
             __syncthreads();
+            V4_TICK(19);
             nd = c.ndec[tid];
             const int changed = __syncthreads_or(marked && ((nd ^ mydec) & kV4DecCmp) != 0);
             c.dec[tid] = nd;
@@ -1211,13 +1255,12 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 wcnt[32 * 256 + tid] = (uint16_t) run;
             } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
             else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
-            if (warp >= 10) {                                             // carried word MRU: 22 warps share the 256 contexts
-                for (int cq = warp - 10; cq < 256; cq += 22) {
-                    uint32_t v;
-                    if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_carry_warp(c, w, Wn, (uint32_t) cq, lane);
-                    else v = w.rpos >= 0 ? 0u : c.mru[cq];               // no push in this window: the carried state (zeroed by a roll-over)
-                    if (lane == 0) c.mru2[cq] = v;
-                }
+            if (tid >= 512 && tid < 768) {                               // carried word MRU: context c is handled by lane c / 32 of warp 16 + c % 8 ...
+                const int cq = ((tid - 512) & 7) * 32 + ((tid - 512) >> 3);    // ... so that the few contexts with pushes spread over the warps
+                uint32_t v;
+                if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_state(c, w, Wn - 1, (uint32_t) cq);
+                else v = w.rpos >= 0 ? 0u : c.mru[cq];                   // no push in this window: the carried state (zeroed by a roll-over)
+                c.mru2[cq] = v;
             }
 #if defined(ZL_V4_PROFILE)
             atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);

@@ -128,6 +128,8 @@ int main(int argc, char** argv) {
                 if (c.mark[rel]) cntw[v4_ctx_of(kx)]++;
             }
             for (int i = 0; i < 256; i++) c.mcnt[i] = cntw[i];
+            for (int i = 0; i < kV4PfWords; i++) c.pf[i] = 0;
+            for (int rel = 0; rel < kV4W; rel++) if (c.mark[rel]) { uint32_t c3, pw; v4_push_of(c, (uint32_t) (lo + rel), &c3, &pw); const uint32_t h = v4_pf_hash(c3, pw); c.pf[h >> 5] |= 1u << (h & 31u); }
             bool changed = false;
             for (int rel = w.entry - lo; rel < wend - lo; rel++) {
                 if (marked_only && !c.mark[rel]) { c.ndec[rel] = c.dec[rel]; continue; }

@@ -49,3 +49,18 @@ def test_cxx_decode_malformed_throws(cli, oracle):
     (d / "bad.zl").write_bytes(bytes(z))
     r = subprocess.run([exe, "d", str(d / "bad.zl"), str(d / "bad.out")], capture_output=True)
     assert r.returncode == 3 and b"invalid encflag" in r.stderr
+
+
+def test_cxx_api_is_reentrant(tmp_path_factory):
+    """two and four threads inside ONE process call Encode/Decode concurrently (the reference is re-entrant: every call owns its
+    EncodeResource/DecodeResource, src/libzling.cpp:108-163); results must equal the solo runs"""
+    d = tmp_path_factory.mktemp("cxxthr")
+    exe = d / "zl_threads"
+    libdir = os.path.dirname(libzling_b200.lib_path())
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cxx", "zl_threads.cpp"),
+                           "-o", str(exe), "-L", libdir, "-lzling", "-Wl,-rpath," + libdir])
+    data = dict(small_cases())["text_random_text"] + dict(small_cases())["text1m"]
+    (d / "in.bin").write_bytes(data)
+    for n in (2, 4):
+        r = subprocess.run([str(exe), str(d / "in.bin"), str(n)], capture_output=True)
+        assert r.returncode == 0, r.stderr
