@@ -200,6 +200,9 @@ struct V4Ctx {
     uint32_t* cnt; uint32_t* mru; uint32_t* mru2;   // carried: inserts per context before the window, word MRU at the window's entry
     uint32_t* last;                             // host replay only: bucket table of the serial link builder
     int dmax, lmax;
+    int coop;                                   // device only: 1 = the calling WARP evaluates ONE position together (all 32 lanes pass the same
+                                                // arguments and follow the same control flow); the loops over bitset words / compare words of the
+                                                // helpers below then run one word per lane.  0 = plain scalar code (the host replay, one position per thread)
 };
 __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
@@ -211,6 +214,7 @@ __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout&
     c.cnt = (uint32_t*) (smem + L.cnt); c.mru = (uint32_t*) (smem + L.mru); c.mru2 = (uint32_t*) (smem + L.mru2);
     c.last = nullptr;
     c.dmax = L.dmax; c.lmax = L.lmax;
+    c.coop = 0;
 }
 
 // per-window constants (uniform over the CTA)
@@ -276,8 +280,26 @@ inline void v4_bucket_pass_serial(const V4Ctx& c) {
 }
 
 // exact GetCommonLength (lz.cpp:66-89) with both operands inside the byte ring: aligned words of both sides, eight at a time
-ZL_HD int v4_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q) {
+ZL_HD int v4_common_len_ring(const uint32_t* rbw, uint32_t p, uint32_t q, int coop = 0) {
     if (v4_rb32(rbw, p) != v4_rb32(rbw, q)) return 0;
+#if defined(__CUDA_ARCH__)
+    if (coop) {                                                          // one word per lane, 128 bytes per step
+        const uint32_t lane = threadIdx.x & 31u;
+        for (uint32_t n = 4; n < 272; n += 128) {
+            const uint32_t o = n + 4u * lane;
+            const uint32_t d = o < 272u ? v4_rb32(rbw, p + o) ^ v4_rb32(rbw, q + o) : 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, d != 0);
+            if (bal) {
+                const int f = __ffs((int) bal) - 1;
+                const uint32_t df = __shfl_sync(0xffffffffu, d, f);
+                const int l = (int) n + 4 * f + ((__ffs((int) df) - 1) >> 3);
+                return l < kMaxLen ? l : kMaxLen;
+            }
+        }
+        return kMaxLen;
+    }
+#endif
+    (void) coop;
     for (int n = 4; n < 272; n += 32) {
         const uint32_t pa = p + (uint32_t) n, qa = q + (uint32_t) n;
         const uint32_t shp = (pa & 3u) * 8u, shq = (qa & 3u) * 8u, pi = pa >> 2, qi = qa >> 2;
@@ -442,6 +464,14 @@ ZL_HD uint32_t v4_ctxbits(const V4Ctx& c, uint32_t cq, int w) {
 // per-context ranks of ALL positions are only built once per window, after the rounds: v4_head_final)
 ZL_HD uint32_t v4_rank_live(const V4Ctx& c, int rel, uint32_t cq) {
     V4_STAT(1, rel >> 5);
+#if defined(__CUDA_ARCH__)
+    if (c.coop) {                                                        // one bitset word per lane
+        const int lane = threadIdx.x & 31, wl = rel >> 5;
+        uint32_t m = 0;
+        if (lane <= wl) { m = v4_ctxbits(c, cq, lane) & c.mbits[lane]; if (lane == wl) m &= (1u << (rel & 31)) - 1u; }
+        return __reduce_add_sync(0xffffffffu, (uint32_t) __popc(m));
+    }
+#endif
     uint32_t n = 0;
     const int wl = rel >> 5;
     for (int w = 0; w < wl; w++) n += (uint32_t) z4_popc(v4_ctxbits(c, cq, w) & c.mbits[w]);
@@ -503,6 +533,29 @@ ZL_HD uint32_t v4_suffix_live(const V4Ctx& c, int y) {
 // the reference's ring[cq][n] as seen while xrel is decided
 ZL_HD uint64_t v4_live_entry(const V4Ctx& c, int lo, int xrel, uint32_t cq, uint32_t n) {
     const uint32_t ord = (n - c.cnt[cq]) & (kRing - 1);                  // n is pending iff it is insert number 1.. of this window
+#if defined(__CUDA_ARCH__)
+    if (c.coop && ord != 0 && ord <= (uint32_t) kV4N) {                  // the same selection, one bitset word per lane
+        const int lane = threadIdx.x & 31, wl = xrel >> 5;
+        uint32_t m = 0;
+        if (lane <= wl) { m = v4_ctxbits(c, cq, lane) & c.mbits[lane]; if (lane == wl) m &= (1u << (xrel & 31)) - 1u; }
+        const uint32_t pc = (uint32_t) __popc(m);
+        uint32_t incl = pc;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const uint32_t bal = __ballot_sync(0xffffffffu, incl >= ord);
+        if (bal) {
+            const int L = __ffs((int) bal) - 1;
+            const uint32_t before = __shfl_sync(0xffffffffu, incl - pc, L);
+            uint32_t mL = __shfl_sync(0xffffffffu, m, L);
+            for (uint32_t i = 1; i < ord - before; i++) mL &= mL - 1u;
+            const int y = L * 32 + __ffs((int) mL) - 1;
+            return ring_make((uint32_t) (lo + y), c.key[y] >> 21, v4_suffix_live(c, y));
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (ord - total == 1u && v4_ctx_of(c.key[xrel]) == cq) return ring_make((uint32_t) (lo + xrel), c.key[xrel] >> 21, v4_suffix_live(c, xrel));
+        return z4_ld_ring(c.ring + (size_t) cq * kRing + n);
+    }
+#endif
     if (ord != 0 && ord <= (uint32_t) kV4N) {
         // the ord-th position with context cq among the pending ones (marked before xrel; xrel itself comes last)
         uint32_t left = ord;
@@ -627,7 +680,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
             if (visited < D && !done) {
                 visited++;
                 if ((c.key[y] >> 21) == chk) {
-                    const int l = v4_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) (lo + y));
+                    const int l = v4_common_len_ring(c.rbw, (uint32_t) x, (uint32_t) (lo + y), c.coop);
                     if (l > best) { best = l; ref = kV4RefWin | (uint32_t) y; if (best == kMaxLen) done = true; }
                 }
             } else break;
@@ -718,6 +771,30 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
     bool have = false;                // a push whose effectiveness is still unknown (needs the front before it)
     uint32_t a = 0; bool u = false;
     const int whi = xrel >> 5, wlo = elo >> 5;
+#if defined(__CUDA_ARCH__)
+    if (c.coop) {                                                        // one bitset word per lane; the newest push is found with a ballot
+        const int lane = threadIdx.x & 31;
+        uint32_t m = (lane >= wlo && lane <= whi) ? occ[lane] & c.mbits[lane] : 0u;
+        if (lane == whi) m &= 0xffffffffu >> (31 - (xrel & 31));
+        if (lane == wlo) m &= 0xffffffffu << (elo & 31);
+        while (true) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, m != 0);
+            if (!bal) break;
+            const int hw = 31 - __clz((int) bal);
+            const uint32_t mw = __shfl_sync(0xffffffffu, m, hw);
+            const int bq = 31 - __clz((int) mw);
+            if (lane == hw) m &= ~(1u << bq);
+            const int e = hw * 32 + bq;
+            const uint32_t xe = (uint32_t) (w.lo + e);
+            const uint32_t pw = (v4_rb8(c.rbw, xe - 2) << 8) | v4_rb8(c.rbw, xe - 1);
+            if (have && (u || pw != a)) return a | (pw << 16);
+            have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
+        }
+        if (!have) return base;
+        if (u || (base & 0xffffu) != a) return a | (base << 16);
+        return base;
+    }
+#endif
     // words of the window that hold a byte cq at all (occw), between the first possible push and xrel, newest first
     uint32_t words = c.occw[cq] & (0xffffffffu >> (31 - whi)) & (0xffffffffu << wlo);
     int st_words = 0, st_push = 0;
@@ -897,38 +974,6 @@ namespace zl {
 struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[24]; };
 
 __device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
-// Word MRU of context cq after all pushes of the window (the state carried into the next window): v4_mru_state(.., Wn - 1, cq)
-// evaluated by a whole warp, lane = bitset word; every lane returns the same value
-__device__ __forceinline__ uint32_t v4_mru_carry_warp(const V4Ctx& c, const V4Win& w, int Wn, uint32_t cq, int lane) {
-    uint32_t base = c.mru[cq];
-    int elo = w.entry - w.lo + (w.skip_push ? 1 : 0);
-    if (w.rpos >= 0) { base = 0; elo = w.rpos - w.lo + 1; }             // the window holds the roll-over: only later pushes count
-    const int xrel = Wn - 1;
-    if (xrel < elo) return base;
-    uint32_t m = c.occ[cq * kV4Words + lane] & c.mbits[lane];
-    if (lane == (xrel >> 5)) m &= 0xffffffffu >> (31 - (xrel & 31));
-    if (lane > (xrel >> 5)) m = 0;
-    if (lane == (elo >> 5)) m &= 0xffffffffu << (elo & 31);
-    if (lane < (elo >> 5)) m = 0;
-    bool have = false, u = false;
-    uint32_t a = 0;
-    while (true) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, m != 0);
-        if (!bal) break;
-        const int hw = 31 - __clz(bal);
-        const uint32_t mw = __shfl_sync(0xffffffffu, m, hw);
-        const int bq = 31 - __clz(mw);
-        if (lane == hw) m &= ~(1u << bq);
-        const int e = hw * 32 + bq;
-        const uint32_t xe = (uint32_t) (w.lo + e);
-        const uint32_t pw = (v4_rb8(c.rbw, xe - 2) << 8) | v4_rb8(c.rbw, xe - 1);
-        if (have && (u || pw != a)) return a | (pw << 16);
-        have = true; a = pw; u = e == w.entry - w.lo ? w.prev_lit != 0 : c.plit[e] != 0;
-    }
-    if (!have) return base;
-    if (u || (base & 0xffffu) != a) return a | (base << 16);
-    return base;
-}
 // warp 0: per-warp totals arr[0..31] -> exclusive prefix in place, grand total in arr[32] (callers synchronise around it)
 __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
     const int v = arr[lane];
@@ -968,6 +1013,8 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
     c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock; c.base_level = base_level;
     const int ilen = c.ilen;
+    V4Ctx cc = c;                                                        // the same state, evaluated by a whole warp per position
+    cc.coop = 1;
     uint8_t* scratch = smem_raw + L.scratch;
     uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
     uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
@@ -1178,27 +1225,36 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             tprev = r2;
             __syncthreads();
             V4_TICK(13);
-            const int qslot = lane * 32 + warp;                          // queue entry of this thread: entries 0..31 go to 32 different warps
-            if (qslot < s_nq[0]) {
-                const int rel = qhaz[qslot];
+            // stages B, C, D: one queue entry per WARP at a time (cc.coop = 1: the 32 lanes evaluate the entry together)
+            for (int i = warp; i < s_nq[0]; i += 32) {
+                const int rel = qhaz[i];
                 const uint32_t fd = c.fdec[rel];
-                if (v4_hazard(c, rel, fd, c.fx[rel], depth_lazy2(w.level))) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) rel;
-                else if (fd & 511u) c.ndec[rel] = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
-                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+                const bool hz = v4_hazard(cc, rel, fd, c.fx[rel], depth_lazy2(w.level));
+                if (lane == 0) {
+                    if (hz) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) rel;
+                    else if (fd & 511u) c.ndec[rel] = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
+                    else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+                }
             }
             __syncthreads();
             V4_TICK(14);
-            if (qslot < s_nq[1]) {
-                const int rel = qgen[qslot];
+            for (int i = warp; i < s_nq[1]; i += 32) {
+                const int rel = qgen[i];
                 uint32_t rf = 0;
-                const uint32_t len = (uint32_t) v4_probe_general(c, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
-                if (len) c.ndec[rel] = v4_dec_match(len, rf);
-                else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+                const uint32_t len = (uint32_t) v4_probe_general(cc, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
+                if (lane == 0) {
+                    if (len) c.ndec[rel] = v4_dec_match(len, rf);
+                    else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
+                }
             }
             __syncthreads();
             V4_TICK(15);
             if (tid == 0) { s_ph[20] += (unsigned long long) s_nq[0]; s_ph[21] += (unsigned long long) s_nq[1]; s_ph[22] += (unsigned long long) s_nq[2]; }
-            if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
+            for (int i = warp; i < s_nq[2]; i += 32) {
+                const int rel = qmru[i];
+                const uint32_t v = v4_decide_word(cc, w, rel);
+                if (lane == 0) c.ndec[rel] = v;
+            }
             __syncthreads();
             V4_TICK(19);
             nd = c.ndec[tid];
@@ -1255,12 +1311,13 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 wcnt[32 * 256 + tid] = (uint16_t) run;
             } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
             else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
-            if (tid >= 512 && tid < 768) {                               // carried word MRU: context c is handled by lane c / 32 of warp 16 + c % 8 ...
-                const int cq = ((tid - 512) & 7) * 32 + ((tid - 512) >> 3);    // ... so that the few contexts with pushes spread over the warps
-                uint32_t v;
-                if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_state(c, w, Wn - 1, (uint32_t) cq);
-                else v = w.rpos >= 0 ? 0u : c.mru[cq];                   // no push in this window: the carried state (zeroed by a roll-over)
-                c.mru2[cq] = v;
+            if (warp >= 10) {                                             // carried word MRU: 22 warps share the contexts that received a push
+                for (int cq = warp - 10; cq < 256; cq += 22) {
+                    uint32_t v;
+                    if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_state(cc, w, Wn - 1, (uint32_t) cq);
+                    else v = w.rpos >= 0 ? 0u : c.mru[cq];               // no push in this window: the carried state (zeroed by a roll-over)
+                    if (lane == 0) c.mru2[cq] = v;
+                }
             }
 #if defined(ZL_V4_PROFILE)
             atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);
