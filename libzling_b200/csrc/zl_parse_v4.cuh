@@ -843,7 +843,9 @@ ZL_HD uint32_t v4_decide_word(const V4Ctx& c, const V4Win& w, int rel) {   // no
     {   // quick reject: every MRU entry is a word pushed in this window or a carried one (zero after a roll-over)
         const uint32_t base = (w.rpos >= 0 && x >= w.rpos) ? 0u : c.mru[cq];
         const uint32_t h = v4_pf_hash(cq, wd);
-        if (!((c.pf[h >> 5] >> (h & 31u)) & 1u) && (base & 0xffffu) != wd && (base >> 16) != wd) return kV4Lit << 9;
+        const bool inpf = ((c.pf[h >> 5] >> (h & 31u)) & 1u) != 0, inbase = (base & 0xffffu) == wd || (base >> 16) == wd;
+        V4_STAT(6, inpf ? 1 : 0); V4_STAT(7, inbase ? 1 : 0);
+        if (!inpf && !inbase) return kV4Lit << 9;
     }
     const uint32_t m = v4_mru_state(c, w, rel, cq);
     const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
@@ -870,11 +872,9 @@ ZL_HD uint32_t v4_decide(const V4Ctx& c, const V4Win& w, int rel, uint32_t* prof
     const uint32_t p2 = V4_PROF_T();
     if (prof) { prof[0] = p1 - p0; prof[1] = p2 - p1; prof[2] = 0; }
     if (len) return len | (kV4Match << 9) | (ref << 12);
-    const uint32_t m = v4_mru_state(c, w, rel, v4_ctx_of(c.key[rel]));  // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
-    const uint32_t wd = (v4_rb8(c.rbw, (uint32_t) x) << 8) | v4_rb8(c.rbw, (uint32_t) x + 1);
-    const uint32_t kind = (m & 0xffffu) == wd ? kV4Word0 : ((m >> 16) == wd ? kV4Word1 : kV4Lit);
+    const uint32_t kd = v4_decide_word(c, w, rel);                      // lz.cpp:172-185 (x + 1 < ilen holds in the probe region)
     if (prof) prof[2] = V4_PROF_T() - p2;
-    return kind << 9;
+    return kd;
 }
 
 // ---- FINALIZE (the rank table is valid now) ------------------------------------------------------------------------------------
@@ -1023,14 +1023,42 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     uint16_t* qgen = qhaz + kV4T;                                                   //         for the full probe on the pending view,
     uint16_t* qmru = qgen + kV4T;                                                   //         for the word-MRU test
 
-    for (int i = tid; i < 256; i += kV4T) { c.cnt[i] = 0; c.mru[i] = 0; }
+    for (int i = tid; i < 256; i += kV4T) { c.cnt[i] = 0; c.mru[i] = 0; c.pcnt[i] = 0; }
+    // Level of the block's FIRST sub-block when the host left it open (blocks after the first of a call): the reference
+    // carries it over from the last sub-block of the previous block (current_level outlives the block loop,
+    // src/libzling.cpp:185,261-266), which is being parsed by another CTA right now.  Predict it from the order-0 entropy of
+    // the previous block's last 64 KiB: data that Huffman cannot shrink below 0.95 of its size (the reference's rule) has
+    // a near-uniform byte histogram.  The host verifies the level afterwards and re-parses on a wrong guess.
+    int level0_pred = base_level;
+    if (b > 0 && a.plan[(size_t) b * kMaxSubPerBlock] == kV4Auto && base_level != 0) {
+        __syncthreads();
+        const uint8_t* tail = c.in - 65536;                              // the previous block's tail (blocks are contiguous, full except the last)
+        for (int i = tid * 16; i < 65536; i += kV4T * 16) {
+            const uint4 v = z4_ld_in128(reinterpret_cast<const uint4*>(tail + i));
+            const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
+            #pragma unroll
+            for (int q = 0; q < 16; q++) atomicAdd(&c.pcnt[(wv[q >> 2] >> ((q & 3) * 8)) & 0xffu], 1u);
+        }
+        __syncthreads();
+        float part = 0.f;
+        if (tid < 256) { const float n = (float) c.pcnt[tid]; part = n > 0.f ? n * __log2f(n) : 0.f; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __shared__ float s_ent[8];
+        if (tid < 256 && lane == 0) s_ent[warp] = part;
+        __syncthreads();
+        float sum = 0.f;
+        for (int i = 0; i < 8; i++) sum += s_ent[i];
+        const float H = 16.f - sum / 65536.f;                            // bits per byte
+        if (H > 7.6f) level0_pred = 0;
+    }
     long long cyc_spec = 0, cyc_rounds = 0, cyc_final = 0, cyc_orbit = 0, cyc_rank = 0, cyc_decide = 0;
     unsigned long long n_rounds = 0, n_windows = 0;
     const long long t_begin = clock64();
     if (tid == 0) {
         V4Run r;
         r.ip = 0; r.op = 0; r.j = 0; r.tok_begin = 0; r.enc_begin = 0; r.prev_lit = 0; r.skip_push = 1; r.tail = 0;
-        r.level = v4_next_level(c, 0, 0, 0);
+        r.level = c.plan[0] == kV4Auto ? level0_pred : v4_next_level(c, 0, 0, 0);
         int nt = 0;
         for (int first = 0; first < 2; first++) {                        // first two bytes raw, lz.cpp:150-151
             if (r.ip == first && r.ip < ilen) { c.tok[nt++] = tok_literal(c.in[r.ip], 0, true); r.op++; r.ip++; }

@@ -221,8 +221,8 @@ int main(int argc, char** argv) {
     printf("\n");
     (void) st_general;
 #if defined(ZL_V4_STATS)
-    const char* names[8] = { "link_hazard steps", "rank_live words", "mru words", "mru pushes", "general calls", "stale replays", "", "" };
-    for (int k = 0; k < 6; k++) {
+    const char* names[8] = { "link_hazard steps", "rank_live words", "mru words", "mru pushes", "general calls", "stale replays", "word: in bloom", "word: in carried" };
+    for (int k = 0; k < 8; k++) {
         printf("  %-18s calls %llu (%.2f/window) mean %.2f max %llu  hist(<1,<2,<4,..):", names[k], g_v4stats.calls[k], (double) g_v4stats.calls[k] / (st_windows ? st_windows : 1),
                g_v4stats.calls[k] ? (double) g_v4stats.steps[k] / g_v4stats.calls[k] : 0.0, g_v4stats.maxsteps[k]);
         for (int b = 0; b < 12; b++) printf(" %llu", g_v4stats.hist[k][b]);
