@@ -113,6 +113,14 @@ def test_level_feedback_replay_happens(ctx, oracle, small):
     assert z == oracle.encode(data, 4)
     data = dict(block_boundary_cases())["random_across_boundary"]
     z = ctx.encode(data, 2)
+    assert z == oracle.encode(data, 2)              # (the block-start level is predicted from the previous block's tail: usually right here)
+    # force a wrong block-start prediction: the first block ENDS with 64 KiB of random bytes (so its tail looks incompressible)
+    # inside a sub-block that compresses well as a whole (so the reference keeps the requested level for the next block)
+    base = np.frombuffer(dict(block_boundary_cases())["blk_plus_tail"], dtype=np.uint8)
+    rnd = np.random.default_rng(3).integers(0, 256, 65536, dtype=np.uint8)
+    blk = libzling_b200.BLOCK
+    data = np.concatenate([base[:blk - 65536], rnd, base[blk - 65536:blk - 65536 + 300000]]).tobytes()
+    z = ctx.encode(data, 2)
     assert z == oracle.encode(data, 2)
     assert ctx.stats()["reparsed_blocks"] >= 1      # the speculated level was wrong at least once and got repaired
 
