@@ -153,20 +153,18 @@ typedef struct {
     uint32_t reparsed_blocks; /* blocks parsed again because the level-feedback prediction was wrong */
     uint64_t tokens;          /* tokens produced by the last call */
     uint64_t subblocks;
-    uint64_t slow_main;       /* parse: probes redone exactly on the live structure (stale record) */
-    uint64_t slow_lazy;       /* parse: lazy probes redone exactly */
-    uint64_t window_hits;     /* parse: candidates served by the in-window mini dictionary */
-    uint64_t windows;         /* parse: speculate/resolve windows executed */
-    uint64_t cyc_spec;        /* parse: SM cycles spent in the speculate phase, summed over blocks */
-    uint64_t cyc_resolve;     /* parse: SM cycles spent in the resolve phase, summed over blocks */
-    uint64_t general_path;    /* parse: tokens resolved through the in-window candidate path instead of the frozen decision */
-    uint64_t cyc_total;       /* parse v3: SM cycles from kernel start to end, summed over blocks */
-    uint64_t flagged;         /* parse v3: tokens whose decision carried a hazard flag (checked; most stay frozen) */
-    uint64_t rounds;          /* parse v4: fixed-point rounds executed, summed over windows and blocks */
-    uint64_t cyc_final;       /* parse v4: SM cycles in FINALIZE (bucket writes, token emission), summed over blocks */
-    uint64_t cyc_orbit;       /* parse v4: SM cycles of the rounds spent on the orbit (pointer doubling) */
-    uint64_t cyc_rank;        /* parse v4: ... on the per-context ranks */
-    uint64_t cyc_decide;      /* parse v4: ... on re-deriving the decisions */
+    uint64_t slow_main, slow_lazy, window_hits;   /* unused (kept for ABI stability of the struct) */
+    uint64_t windows;         /* parse: windows of 1022 positions executed, summed over blocks */
+    uint64_t cyc_spec;        /* parse: SM cycles spent in SPEC (records against the frozen bucket state), summed over blocks */
+    uint64_t cyc_resolve;     /* parse: SM cycles spent in the fixed-point ROUNDS, summed over blocks */
+    uint64_t general_path;    /* unused */
+    uint64_t cyc_total;       /* parse: SM cycles from kernel start to end, summed over blocks */
+    uint64_t flagged;         /* unused */
+    uint64_t rounds;          /* parse: fixed-point rounds executed, summed over windows and blocks */
+    uint64_t cyc_final;       /* parse: SM cycles in FINALIZE (bucket writes, token emission), summed over blocks */
+    uint64_t cyc_orbit;       /* parse: SM cycles of the rounds spent on the orbit of the entry position */
+    uint64_t cyc_rank;        /* parse: ... on the sub-block roll-over scan */
+    uint64_t cyc_decide;      /* parse: ... on re-deriving the decisions of the marked positions */
 } zlb_stats;
 int zlb_get_stats(const zlb_ctx* ctx, zlb_stats* out);
 

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzling.so")
 SOURCES = ["zl_engine.cu", "zl_api.cpp"]
-DEPS = SOURCES + ["zl_kernels.cu", "zl_shard.cuh", "zl_mtf_walk.h", "zl_kernels.cuh", "zl_parse_v2.cuh", "zl_parse_v3.cuh", "zl_parse_v4.cuh", "zl_tables.h", "../../include/zlb.h",
+DEPS = SOURCES + ["zl_kernels.cu", "zl_shard.cuh", "zl_mtf_walk.h", "zl_kernels.cuh", "zl_parse_v4.cuh", "zl_tables.h", "../../include/zlb.h",
                   "../../include/libzling/libzling.h", "../../include/libzling/libzling_utils.h"]
 
 
@@ -36,8 +36,6 @@ def build(force=False, verbose=False):
         cmd += ["-Xptxas", "-v"]
     if os.environ.get("ZL_V4_PROFILE"):       # profiling build: per-thread timers inside the parse kernel's decide step
         cmd += ["-DZL_V4_PROFILE=1"]
-    if os.environ.get("ZL_V3_PROD"):          # experiment knob: producer threads of the parse kernel (default in zl_parse_v3.cuh)
-        cmd += ["-DZL_V3_PROD=" + os.environ["ZL_V3_PROD"]]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -63,14 +63,7 @@ struct zlb_ctx {
     cudaEvent_t ev[EV_COUNT] = {};
     zlb_stats stats = {};
     int last_nblocks = 0;
-    int parse_version = 4;          // ZLB_PARSE=1: literal one-warp-per-block chain walker, 2: windowed speculate/resolve, 3: pipelined one-thread resolver, 4: fixed-point iteration over 1024-position windows (default)
     const void* pending = nullptr;  // encoder with a submitted, not yet completed range: it owns the context's buffers
-    int v3_serialize = 0;           // ZLB_V3_SERIAL=1: experiment, run RESOLVE(k) after SPEC(k+1) instead of concurrently
-    int mtf_version = 2;            // ZLB_MTF=1: one warp per stream, 2: one CTA per context (default)
-    V2Counters* d_v2c = nullptr;
-    V2Counters  h_v2c = {};
-    V3Counters* d_v3c = nullptr;
-    V3Counters  h_v3c = {};
     V4Counters* d_v4c = nullptr;
     V4Counters  h_v4c = {};
     uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
@@ -125,8 +118,8 @@ void zlb_destroy(zlb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* dev[] = { c->d_in, c->d_out, c->d_ring, c->d_hash, c->d_tok, c->d_lit, c->d_sub, c->d_tab, c->d_nsub, c->d_ntok, c->d_nlit,
-                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp, c->d_v2c,
-                    c->d_v3c, c->d_v4c, c->d_lbuf, c->d_lhist, c->d_ctxoff };
+                    c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp,
+                    c->d_v4c, c->d_lbuf, c->d_lhist, c->d_ctxoff };
     for (void* p : dev) if (p) cudaFree(p);
     void* host[] = { c->h_sub, c->h_nsub, c->h_ntok, c->h_nlit, c->h_ilen, c->h_plan, c->h_active, c->h_active2, c->h_outoff, c->h_status };
     for (void* p : host) if (p) cudaFreeHost(p);
@@ -165,23 +158,15 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaHostAlloc(&c->h_active2, nb, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_outoff, nsb * sizeof(unsigned long long), cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + 4) * sizeof(int), cudaHostAllocDefault));
-    CU(cudaMalloc(&c->d_v2c, sizeof(V2Counters)));
-    CU(cudaMalloc(&c->d_v3c, sizeof(V3Counters)));
     CU(cudaMalloc(&c->d_v4c, sizeof(V4Counters)));
     CU(cudaMalloc(&c->d_lbuf, nb * kLitStride * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_lhist, nb * (size_t) kLitUnitsMax * 256 * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_ctxoff, nb * 257 * sizeof(uint32_t)));
-    CU(cudaFuncSetAttribute(zl_rolz_parse_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CU(cudaFuncSetAttribute(zl_rolz_parse_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v3_layout(depth_main(4), depth_lazy1(4)).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(2, 1).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(4, 1).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(8, 3).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(16, 4).total));
-    { const char* pv = getenv("ZLB_PARSE"); if (pv && *pv >= '1' && *pv <= '4') c->parse_version = *pv - '0'; }
-    { const char* pv = getenv("ZLB_V3_SERIAL"); if (pv && *pv == '1') c->v3_serialize = 1; }
-    { const char* pv = getenv("ZLB_MTF"); if (pv && *pv >= '1' && *pv <= '2') c->mtf_version = *pv - '0'; }
-    CU(cudaFuncSetAttribute(zl_mtf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     return ZLB_OK;
@@ -270,8 +255,8 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         for (int b = 0; b < nb; b++) {
             c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
             c->h_active[b] = 1;
-            // v3 predicts the level of a sub-block from the previous one (kPlanAuto); v1/v2 get explicit levels
-            memset(c->h_plan + (size_t) b * kMaxSubPerBlock, c->parse_version >= 3 ? (int) kPlanAuto : e->level, kMaxSubPerBlock);
+            // the parse predicts the level of every sub-block the host has not pinned (kV4Auto, zl_parse_v4.cuh: v4_next_level)
+            memset(c->h_plan + (size_t) b * kMaxSubPerBlock, (int) kV4Auto, kMaxSubPerBlock);
         }
         c->h_plan[0] = (uint8_t) e->cur_level;                    // current_level outlives blocks, libzling.cpp:185
         CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
@@ -297,9 +282,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(c->ev[EV_PARSE0], st));
         zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
-        if (c->parse_version == 1) {
-            zl_rolz_parse_kernel<<<nb, 32, 0, st>>>(pa);
-        } else if (c->parse_version == 4) {
+        {
             const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
             const V4Layout lay = v4_layout(dmax, lmax);
             if (pass == 0) CU(cudaMemsetAsync(c->d_v4c, 0, sizeof(V4Counters), st));
@@ -310,25 +293,12 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
                 case 3:  zl_rolz_parse_v4_kernel<8, 3><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
                 default: zl_rolz_parse_v4_kernel<16, 4><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
             }
-        } else if (c->parse_version == 3) {
-            const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
-            const V3Layout lay = v3_layout(dmax, lmax);
-            if (pass == 0) CU(cudaMemsetAsync(c->d_v3c, 0, sizeof(V3Counters), st));
-            zl_rolz_parse_v3_kernel<<<nb, kV3Threads, lay.total, st>>>(pa, dmax, lmax, e->level, c->v3_serialize, c->d_v3c);
-        } else {
-            const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
-            const int W = e->level <= 2 ? 1024 : 512;
-            const V2Layout lay = v2_layout(W, dmax, lmax);
-            if (pass == 0) CU(cudaMemsetAsync(c->d_v2c, 0, sizeof(V2Counters), st));
-            zl_rolz_parse_v2_kernel<<<nb, kV2Threads, lay.total, st>>>(pa, W, dmax, lmax, e->level, c->d_v2c);
         }
         CU(cudaEventRecord(c->ev[EV_PARSE1], st));
         launches += 2; parse_launches += 1;
         }
         if (mode == MODE_SUBMIT) { CU(cudaGetLastError()); return ZLB_OK; }
-        if (c->mtf_version == 1) {
-            zl_mtf_rank_kernel<<<1, 32, 131072, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, nb, state_in, state_out, c->d_ckpt);
-        } else {
+        {
             const dim3 lgrid(kLitUnitsMax / kLitWarps, nb - first_dirty);
             zl_lit_count_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, c->d_lhist);
             zl_lit_scan_kernel<<<nb - first_dirty, 256, 0, st>>>(c->d_nlit, first_dirty, c->d_lhist, c->d_ctxoff);
@@ -371,13 +341,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
                 if (bad_j < 0 && (int) sb.level != cur) {
                     bad_j = j;
                     plan[j] = (uint8_t) cur;
-                    for (int q = j + 1; q < kMaxSubPerBlock; q++) plan[q] = c->parse_version >= 3 ? (uint8_t) kPlanAuto : (uint8_t) e->level;
-                    if (c->parse_version < 3) {                      // v1/v2 cannot predict: guess from how the wrong run compressed
-                        for (int q = j + 1; q < kMaxSubPerBlock; q++) {
-                            const bool prev_bad = q - 1 < ns && incompressible(c->h_sub[(size_t) b * kMaxSubPerBlock + q - 1]);
-                            plan[q] = prev_bad ? 0 : (uint8_t) e->level;
-                        }
-                    }
+                    for (int q = j + 1; q < kMaxSubPerBlock; q++) plan[q] = (uint8_t) kV4Auto;
                 } else if (bad_j < 0 && exact) {
                     plan[j] = (uint8_t) sb.level;                     // verified: pin it for any later re-parse of this block
                 }
@@ -423,7 +387,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
     c->stats.cyc_spec = c->stats.cyc_resolve = c->stats.general_path = 0;
     c->stats.cyc_total = 0; c->stats.flagged = 0;
     c->stats.rounds = 0; c->stats.cyc_final = c->stats.cyc_orbit = c->stats.cyc_rank = c->stats.cyc_decide = 0;
-    if (c->parse_version == 4) {
+    {
         CU(cudaMemcpyAsync(&c->h_v4c, c->d_v4c, sizeof(V4Counters), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         c->stats.windows = c->h_v4c.windows; c->stats.rounds = c->h_v4c.rounds;
@@ -435,19 +399,6 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             for (int i = 0; i < 24; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
             fprintf(stderr, "\n");
         }
-    } else if (c->parse_version == 3) {
-        CU(cudaMemcpyAsync(&c->h_v3c, c->d_v3c, sizeof(V3Counters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        c->stats.slow_main = c->h_v3c.slow; c->stats.window_hits = c->h_v3c.linkwalk; c->stats.windows = c->h_v3c.windows;
-        c->stats.cyc_spec = c->h_v3c.cyc_spec; c->stats.cyc_resolve = c->h_v3c.cyc_resolve; c->stats.general_path = c->h_v3c.general;
-        c->stats.cyc_total = c->h_v3c.cyc_total; c->stats.flagged = c->h_v3c.flagged;
-        if (getenv("ZLB_V3_TRACE")) fprintf(stderr, "v3: tokens %llu resolve %llu special %llu cycles, flagged %llu general %llu slow %llu\n", c->h_v3c.tokens, c->h_v3c.cyc_resolve, c->h_v3c.cyc_special, c->h_v3c.flagged, c->h_v3c.general, c->h_v3c.slow);
-    } else if (c->parse_version == 2) {
-        CU(cudaMemcpyAsync(&c->h_v2c, c->d_v2c, sizeof(V2Counters), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        c->stats.slow_main = c->h_v2c.slow_main; c->stats.slow_lazy = c->h_v2c.slow_lazy;
-        c->stats.window_hits = c->h_v2c.md_hits; c->stats.windows = c->h_v2c.windows;
-        c->stats.cyc_spec = c->h_v2c.cyc_spec; c->stats.cyc_resolve = c->h_v2c.cyc_resolve; c->stats.general_path = c->h_v2c.general;
     }
     return ZLB_OK;
 }

@@ -31,281 +31,10 @@ __global__ void zl_reset_buckets_kernel(uint64_t* ring, uint16_t* hash, const ui
     }
 }
 
-// =====================================================================================================
-// ROLZ parse
-// =====================================================================================================
-// unaligned little-endian 32-bit load built from two aligned words (HashContext's unaligned load,
-// src/libzling_lz.cpp:55-57); `base` is 4-byte aligned and readable 8 bytes past any offset used
-__device__ __forceinline__ uint32_t ld32u(const uint8_t* base, uint32_t off) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(base) + (off >> 2);
-    const uint32_t lo = __ldg(w), hi = __ldg(w + 1);
-    return __funnelshift_r(lo, hi, (off & 3u) * 8u);
-}
-__device__ __forceinline__ uint32_t ctx_hash(uint32_t w) {                 // lz.cpp:55-57
-    return w + ((w >> 16) & 0xffu) * 137u + (w >> 24) * 13337u;
-}
-
-// GetCommonLength (lz.cpp:66-89) as one warp-wide sweep: lane l compares bytes [8l, 8l+8); 0 if < 4 bytes agree
-__device__ __forceinline__ int warp_common_len(const uint8_t* in, uint32_t p, uint32_t q, int lane) {
-    const uint32_t o = (uint32_t) lane * 8u;
-    const uint32_t x0 = ld32u(in, p + o) ^ ld32u(in, q + o);
-    const uint32_t x1 = ld32u(in, p + o + 4) ^ ld32u(in, q + o + 4);
-    const int n = x0 ? ((__ffs(x0) - 1) >> 3) : (x1 ? 4 + ((__ffs(x1) - 1) >> 3) : 8);
-    const uint32_t miss = __ballot_sync(0xffffffffu, n < 8);
-    int len;
-    if (miss == 0) {                                                     // 256 bytes agree: look at 256..258
-        const uint32_t xt = ld32u(in, p + 256) ^ ld32u(in, q + 256);
-        const int t = xt ? ((__ffs(xt) - 1) >> 3) : 4;
-        len = 256 + (t < 3 ? t : 3);
-    } else {
-        const int first = __ffs(miss) - 1;
-        len = first * 8 + __shfl_sync(0xffffffffu, n, first);
-    }
-    return len < kMinLen ? 0 : len;
-}
-
-struct ParseCtx {
-    const uint8_t* in;
-    uint64_t*      ring;
-    uint16_t*      hash;
-    uint16_t*      head;    // shared: ring head per context
-    int            lane;
-};
-
-// MatchLazy, lz.cpp:291-316
-__device__ __forceinline__ bool lazy_probe(const ParseCtx& k, uint32_t pos, int best, int depth) {
-    const int c = k.in[pos - 1];
-    const uint32_t slot = ctx_hash(ld32u(k.in, pos)) & (kSlots - 1);
-    int node = k.hash[(size_t) c * kSlots + slot];
-    if (node == kNil) return false;
-    const uint64_t* rc = k.ring + (size_t) c * kRing;
-    const uint32_t at = (uint32_t) best - 3u;
-    const uint32_t mine = ld32u(k.in, pos + at);
-    uint64_t e = rc[node];
-    for (int hop = 0; hop < depth; hop++) {
-        const uint32_t cand = ring_pos(e);
-        if (ld32u(k.in, cand + at) == mine) return true;
-        const int nxt = ring_suffix(e);
-        if (nxt == kNil) break;
-        const uint64_t e2 = rc[nxt];
-        if (cand <= ring_pos(e2)) break;
-        e = e2;
-    }
-    return false;
-}
-
-// MatchAndUpdate, lz.cpp:211-289: insert first, then walk the chain; returns match length (0 = none)
-__device__ __forceinline__ int probe_and_insert(const ParseCtx& k, uint32_t pos, int level, int* idx_out) {
-    const uint32_t h = ctx_hash(ld32u(k.in, pos));
-    const uint32_t check = (h >> 13) & 0xffu, slot = h & (kSlots - 1);
-    const int c = k.in[pos - 1];
-    uint16_t* hslot = k.hash + (size_t) c * kSlots + slot;
-    uint64_t* rc = k.ring + (size_t) c * kRing;
-    int node = *hslot;
-    const int head = (k.head[c] + 1) & (kRing - 1);
-    __syncwarp();
-    if (k.lane == 0) {                                                   // lz.cpp:227-230
-        k.head[c] = (uint16_t) head;
-        rc[head] = ring_make(pos, check, (uint32_t) node);
-        *hslot = (uint16_t) head;
-    }
-    __syncwarp();
-    if (node == kNil || node == head) return 0;                          // lz.cpp:234-237
-
-    int best = kMinLen - 1, bestnode = 0;
-    const int depth = depth_main(level);
-    uint64_t e = rc[node];
-    for (int hop = 0; hop < depth; hop++) {                              // lz.cpp:240-267
-        const uint32_t cand = ring_pos(e);
-        if (ring_check(e) == check) {
-            const int l = warp_common_len(k.in, pos, cand, k.lane);
-            if (l > best) {
-                best = l; bestnode = node;
-                if (best == kMaxLen) break;
-            }
-        }
-        const int nxt = ring_suffix(e);
-        if (nxt == kNil) break;
-        const uint64_t e2 = rc[nxt];
-        if (cand <= ring_pos(e2)) break;
-        node = nxt; e = e2;
-    }
-    if (best < kMinLen) return 0;
-    if (best < kLazyBelow) {                                             // lz.cpp:270-281
-        const int l1 = depth_lazy1(level), l2 = depth_lazy2(level);
-        if (lazy_probe(k, pos + 1, best, l1)) return 0;
-        if (l2 > 0 && lazy_probe(k, pos + 2, best, l2)) return 0;
-    }
-    *idx_out = (head - bestnode) & (kRing - 1);                          // lz.cpp:283
-    return best;
-}
-
-// One warp per 16 MiB block walks the serial token chain (EncodeImpl, lz.cpp:139-195): control flow is
-// warp-uniform, lanes split the byte comparison; lane 0 owns every store.
-__global__ void __launch_bounds__(32) zl_rolz_parse_kernel(ParseArgs a) {
-    const int b = blockIdx.x, lane = threadIdx.x;
-    if (!a.active[b]) return;
-    __shared__ uint16_t s_head[256];
-    __shared__ uint32_t s_mru[256];          // word MRU per context: low half = slot 0, high half = slot 1
-
-    const uint8_t* in = a.in + (size_t) b * kBlockBytes;
-    const int ilen = (int) a.ilen[b];
-    uint32_t* tok = a.tok + (size_t) b * kTokStride;
-    uint32_t* lit = a.lit + (size_t) b * kLitStride;
-    SubBlock* sub = a.sub + (size_t) b * kMaxSubPerBlock;
-    const uint8_t* plan = a.plan + (size_t) b * kMaxSubPerBlock;
-
-    ParseCtx k;
-    k.in = in; k.ring = a.ring + (size_t) b * kRingStride; k.hash = a.hash + (size_t) b * kHashStride;
-    k.head = s_head; k.lane = lane;
-    for (int i = lane; i < 256; i += 32) s_head[i] = 0;
-
-    int ip = 0, nt = 0, nl = 0, j = 0;
-    while (ip < ilen) {
-        const int level = plan[j < kMaxSubPerBlock ? j : kMaxSubPerBlock - 1];
-        for (int i = lane; i < 256; i += 32) s_mru[i] = 0;               // zeroed every sub-block, lz.cpp:147
-        __syncwarp();
-        int op = 0;
-        const int tok_begin = nt, enc_begin = ip;
-        for (int first = 0; first < 2; first++) {                        // lz.cpp:150-151
-            if (ip == first && ip < ilen) {
-                if (lane == 0) tok[nt] = tok_literal(in[ip], 0, true);
-                nt++; op++; ip++;
-            }
-        }
-        while (op + 1 < kSubSymbols && ip < ilen) {                      // lz.cpp:153
-            if (ip + kGuard < ilen) {                                    // lz.cpp:158
-                int idx = 0;
-                const int l = probe_and_insert(k, (uint32_t) ip, level, &idx);
-                if (l) {
-                    if (lane == 0) tok[nt] = tok_match((uint32_t) l, (uint32_t) idx);
-                    nt++; op += 2; ip += l;
-                    const int c = in[ip - 3];
-                    const uint32_t w = ((uint32_t) in[ip - 2] << 8) | in[ip - 1];
-                    const uint32_t m = s_mru[c];
-                    __syncwarp();
-                    if (lane == 0 && (m & 0xffffu) != w) s_mru[c] = w | (m << 16);   // lz.cpp:163-166
-                    __syncwarp();
-                    continue;
-                }
-            }
-            if (ip + 1 < ilen) {                                         // lz.cpp:172-185
-                const int c = in[ip - 1];
-                const uint32_t w = ((uint32_t) in[ip] << 8) | in[ip + 1];
-                const uint32_t m = s_mru[c];
-                if ((m & 0xffffu) == w) {
-                    if (lane == 0) tok[nt] = tok_word(0);
-                    nt++; op++; ip += 2;
-                    continue;
-                }
-                if ((m >> 16) == w) {
-                    if (lane == 0) tok[nt] = tok_word(1);
-                    nt++; op++; ip += 2;
-                    __syncwarp();
-                    if (lane == 0) s_mru[c] = w | (m << 16);
-                    __syncwarp();
-                    continue;
-                }
-            }
-            if (lane == 0) {                                             // literal, lz.cpp:188
-                tok[nt] = tok_literal(in[ip], in[ip - 1], false);
-                lit[nl] = (uint32_t) nt;
-            }
-            nt++; nl++; op++; ip++;
-            {
-                const int c = in[ip - 3];                                // lz.cpp:190-191
-                const uint32_t w = ((uint32_t) in[ip - 2] << 8) | in[ip - 1];
-                const uint32_t m = s_mru[c];
-                __syncwarp();
-                if (lane == 0) s_mru[c] = w | (m << 16);
-                __syncwarp();
-            }
-        }
-        if (lane == 0 && j < kMaxSubPerBlock) {
-            SubBlock s;
-            s.tok_begin = tok_begin; s.tok_end = nt; s.enc_begin = enc_begin; s.enc_end = ip;
-            s.rlen = op; s.level = level; s.olen = 0; s.bits_lo = 0;
-            sub[j] = s;
-        }
-        j++;
-    }
-    if (lane == 0) { a.nsub[b] = j; a.ntok[b] = nt; a.nlit[b] = nl; }
-}
-
 }  // namespace zl
-#include "zl_parse_v2.cuh"
-#include "zl_parse_v3.cuh"
+
 #include "zl_parse_v4.cuh"
 namespace zl {
-
-// =====================================================================================================
-// MTF rank pass (stream order, state carried across blocks and calls)
-// =====================================================================================================
-// One warp per stream.  32 literals at a time: literals of different contexts are independent and are
-// ranked by different lanes at once; literals sharing a context are serialised in stream order ("rounds").
-// sym/rank tables of all 256 contexts (128 KiB) live in shared memory.
-__global__ void __launch_bounds__(32) zl_mtf_rank_kernel(uint32_t* tok_all, const uint32_t* lit_all, const uint32_t* nlit,
-                                                         int first_block, int nblocks, const uint8_t* state_in /*65536 B*/,
-                                                         uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
-    extern __shared__ uint8_t smem[];
-    uint8_t* s_sym = smem;            // [ctx][rank] -> byte
-    uint8_t* s_rank = smem + 65536;   // [ctx][byte] -> rank
-    const int lane = threadIdx.x;
-    {   // load carried state
-        // block 0 starts from the state carried into this call; a replay from block k > 0 (level-feedback
-        // re-parse) starts from the checkpoint the previous pass left for block k
-        const uint4* src = reinterpret_cast<const uint4*>(first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536);
-        uint4* dst = reinterpret_cast<uint4*>(s_sym);
-        for (int i = lane; i < 65536 / 16; i += 32) dst[i] = src[i];
-        __syncwarp();
-        for (int i = lane; i < 65536; i += 32) s_rank[(i & 0xff00) | s_sym[i]] = (uint8_t) (i & 0xff);
-        __syncwarp();
-    }
-    for (int b = first_block; b < nblocks; b++) {
-        {     // MTF state at the start of block b (replay point for level-feedback re-parses)
-            uint4* dst = reinterpret_cast<uint4*>(checkpoints + (size_t) b * 65536);
-            const uint4* src = reinterpret_cast<const uint4*>(s_sym);
-            for (int i = lane; i < 65536 / 16; i += 32) dst[i] = src[i];
-        }
-        uint32_t* tok = tok_all + (size_t) b * kTokStride;
-        const uint32_t* lit = lit_all + (size_t) b * kLitStride;
-        const int n = (int) nlit[b];
-        // software pipeline: fetch group g+1 while ranking group g
-        uint32_t ti_next = 0, t_next = 0;
-        if (lane < n) { ti_next = lit[lane]; t_next = tok[ti_next]; }
-        for (int base = 0; base < n; base += 32) {
-            const uint32_t ti = ti_next, t = t_next;
-            const bool live = base + lane < n;
-            if (base + 32 + lane < n) { ti_next = lit[base + 32 + lane]; t_next = tok[ti_next]; }
-            const int ctx = live ? (int) tok_aux(t) & 0xff : 256 + lane;      // dead lanes get unique keys
-            const int byte = (int) tok_byte(t);
-            const uint32_t same = __match_any_sync(0xffffffffu, ctx);
-            const int order = __popc(same & ((1u << lane) - 1u));
-            int rounds = __popc(same);
-            for (int d = 16; d > 0; d >>= 1) rounds = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, d));
-            int rank = 0;
-            for (int r = 0; r < rounds; r++) {
-                if (live && order == r) {                                 // lz.cpp:112-117
-                    uint8_t* sy = s_sym + ctx * 256;
-                    uint8_t* rk = s_rank + ctx * 256;
-                    const int i = rk[byte], jn = mtf_next(i);
-                    const int other = sy[jn];
-                    sy[i] = (uint8_t) other; sy[jn] = (uint8_t) byte;
-                    rk[other] = (uint8_t) i; rk[byte] = (uint8_t) jn;
-                    rank = i;
-                }
-                __syncwarp();
-            }
-            if (live) tok[ti] = (t & ~kTokSymMask) | (uint32_t) rank;
-        }
-    }
-    __syncwarp();
-    {
-        uint4* dst = reinterpret_cast<uint4*>(state_out);
-        const uint4* src = reinterpret_cast<const uint4*>(s_sym);
-        for (int i = lane; i < 65536 / 16; i += 32) dst[i] = src[i];
-    }
-}
 
 // =====================================================================================================
 // MTF rank pass, context-parallel form (zl_lit_count / zl_lit_scan / zl_lit_scatter / zl_mtf_ctx)
