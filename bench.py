@@ -223,7 +223,9 @@ def main():
     nbytes = int(args.size_mb * 1e6)
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        # launched like our arm (torchrun at N > 1: rank 0 works, the others exit); a plain `python bench.py --impl reference
+        # --gpus N` gives the same N-stream workload
+        run_reference(args, rank, world if "WORLD_SIZE" in os.environ else max(1, args.gpus))
         return
 
     import torch

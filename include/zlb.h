@@ -81,6 +81,21 @@ int zlb_encode_blocks(zlb_encoder* enc, const uint8_t* in, size_t n, uint8_t* ou
  * 16 bytes past n. */
 int zlb_encode_blocks_device(zlb_encoder* enc, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len);
 
+/* ---- batch: many independent streams in one call -------------------------------------------------------
+ * The reference encodes one stream per Encode() call (demo/zling.cpp:195-213); a 16 MiB block is one CTA here, so a single short
+ * stream leaves most of the GPU idle.  zlb_encode_batch takes whole streams (each starts from the initial MTF tables and from
+ * current_level = level, exactly like a fresh Encode() call), lays their blocks side by side and runs ONE pass of the pipeline
+ * over all of them: sum of ceil(n / 16 MiB) over the streams must not exceed max_blocks.  out_len is set per stream; the bytes
+ * of every stream equal what Encode() produces for it alone.  zlb_decode_batch is the inverse (each `in` = a whole framed
+ * stream of at most max_blocks blocks in total): one decode chain per stream runs concurrently. */
+typedef struct {
+    const uint8_t* in; size_t n;          /* host: the stream (encode: raw bytes; decode: framed bytes) */
+    uint8_t* out; size_t out_cap;         /* host: where the result goes */
+    size_t out_len;                       /* set by the call */
+} zlb_stream_io;
+int zlb_encode_batch(zlb_ctx* ctx, int level, zlb_stream_io* streams, int nstreams);
+int zlb_decode_batch(zlb_ctx* ctx, zlb_stream_io* streams, int nstreams);
+
 /* Split form for ONE stream sharded over several GPUs (contiguous block ranges per GPU).  The parse of a range does
  * not depend on the MTF tables carried from the previous range, and on the carried level only for its first
  * sub-block (src/libzling.cpp:185,261-266), so: submit = H2D + parse launch (returns at once, assumes the carried level

@@ -39,6 +39,10 @@ class ShardStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class StreamIO(C.Structure):
+    _fields_ = [("inp", C.c_void_p), ("n", C.c_size_t), ("out", C.c_void_p), ("out_cap", C.c_size_t), ("out_len", C.c_size_t)]
+
+
 class SubBlock(C.Structure):
     _fields_ = [(k, C.c_uint32) for k in ("tok_begin", "tok_end", "enc_begin", "enc_end", "rlen", "level", "olen", "bits_lo")]
 
@@ -48,7 +52,8 @@ EXPORTS = ["zlb_device_count", "zlb_create", "zlb_destroy", "zlb_max_blocks", "z
            "zlb_encode_blocks", "zlb_encode_blocks_device", "zlb_encode_submit", "zlb_encode_complete", "zlb_encoder_get_state", "zlb_encoder_set_state",
            "zlb_decoder_begin", "zlb_decoder_end", "zlb_decode_blocks", "zlb_get_stats", "zlb_debug_tokens",
            "zlb_debug_subblocks", "zlb_debug_huff_tables",
-           "zlb_comm_get_unique_id", "zlb_comm_create", "zlb_comm_destroy", "zlb_comm_get_stats", "zlb_encode_stream_sharded", "zlb_encode_blocks_gathered", "zlb_gather_packed"]
+           "zlb_comm_get_unique_id", "zlb_comm_create", "zlb_comm_destroy", "zlb_comm_get_stats", "zlb_encode_stream_sharded", "zlb_encode_blocks_gathered", "zlb_gather_packed",
+           "zlb_encode_batch", "zlb_decode_batch"]
 
 _lib = None
 
@@ -101,6 +106,8 @@ def load():
     L.zlb_comm_get_stats.argtypes = [C.c_void_p, C.POINTER(ShardStats)]
     L.zlb_encode_stream_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.zlb_encode_blocks_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+    L.zlb_encode_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(StreamIO), C.c_int]
+    L.zlb_decode_batch.argtypes = [C.c_void_p, C.POINTER(StreamIO), C.c_int]
     L.zlb_gather_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
     _lib = L
     return L
@@ -203,6 +210,26 @@ class Context:
             return b"".join(parts)
         finally:
             dec.close()
+
+    # -- batch: many independent streams in one call (zlb_encode_batch / zlb_decode_batch) -------------------
+    def _batch(self, streams, caps, call):
+        ins = [_as_u8(x) for x in streams]
+        outs = [np.empty(max(int(cap), 1), dtype=np.uint8) for cap in caps]
+        arr = (StreamIO * len(ins))()
+        for i, (a, o) in enumerate(zip(ins, outs)):
+            arr[i].inp, arr[i].n, arr[i].out, arr[i].out_cap, arr[i].out_len = a.ctypes.data, a.size, o.ctypes.data, o.size, 0
+        _check(call(arr, len(ins)))
+        return [bytes(o[:arr[i].out_len]) for i, o in enumerate(outs)]
+
+    def encode_batch(self, streams, level=0):
+        """whole streams in, framed streams out; all blocks of all streams share one pass of the pipeline"""
+        L = load()
+        return self._batch(streams, [L.zlb_encode_bound(len(_as_u8(x))) for x in streams], lambda arr, n: L.zlb_encode_batch(self._h, level, arr, n))
+
+    def decode_batch(self, streams, raw_sizes):
+        """framed streams in, raw streams out (raw_sizes: upper bounds of the decoded sizes); one decode chain per stream"""
+        L = load()
+        return self._batch(streams, raw_sizes, lambda arr, n: L.zlb_decode_batch(self._h, arr, n))
 
     def stats(self):
         s = Stats()

@@ -67,6 +67,12 @@ struct zlb_ctx {
     V4Counters* d_v4c = nullptr;
     V4Counters  h_v4c = {};
     uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
+    MtfRange *d_mrng = nullptr, *h_mrng = nullptr;   // per-stream block ranges of the MTF pass (max_blocks entries)
+    uint8_t* d_bstate = nullptr;                     // batch API: initial MTF tables + one scratch table per stream, allocated on first use
+    int bstate_streams = 0;
+    DecRange *d_drng = nullptr, *h_drng = nullptr;   // per-stream sub-block ranges of the ROLZ decode (max_blocks entries)
+    uint8_t* d_dstate = nullptr;                     // batch decode: one MTF table set per stream
+    int dstate_streams = 0, decring_streams = 0;
 };
 
 struct zlb_encoder {
@@ -119,8 +125,10 @@ void zlb_destroy(zlb_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* dev[] = { c->d_in, c->d_out, c->d_ring, c->d_hash, c->d_tok, c->d_lit, c->d_sub, c->d_tab, c->d_nsub, c->d_ntok, c->d_nlit,
                     c->d_ilen, c->d_plan, c->d_active, c->d_active2, c->d_ckpt, c->d_outoff, c->d_decsub, c->d_status, c->d_decring, c->d_comp,
-                    c->d_v4c, c->d_lbuf, c->d_lhist, c->d_ctxoff };
+                    c->d_v4c, c->d_lbuf, c->d_lhist, c->d_ctxoff, c->d_mrng, c->d_bstate, c->d_drng, c->d_dstate };
     for (void* p : dev) if (p) cudaFree(p);
+    if (c->h_mrng) cudaFreeHost(c->h_mrng);
+    if (c->h_drng) cudaFreeHost(c->h_drng);
     void* host[] = { c->h_sub, c->h_nsub, c->h_ntok, c->h_nlit, c->h_ilen, c->h_plan, c->h_active, c->h_active2, c->h_outoff, c->h_status };
     for (void* p : host) if (p) cudaFreeHost(p);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -147,8 +155,9 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaMalloc(&c->d_plan, nsb)); CU(cudaMalloc(&c->d_active, nb)); CU(cudaMalloc(&c->d_active2, nb)); CU(cudaMalloc(&c->d_ckpt, (nb + 1) * 65536));
     CU(cudaMalloc(&c->d_outoff, nsb * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->d_decsub, c->decsub_cap * sizeof(DecSub)));
-    CU(cudaMalloc(&c->d_status, (c->decsub_cap + 4) * sizeof(int)));
+    CU(cudaMalloc(&c->d_status, (c->decsub_cap + nb + 4) * sizeof(int)));
     CU(cudaMalloc(&c->d_decring, (size_t) 256 * kRing * sizeof(uint32_t)));
+    c->decring_streams = 1;
     CU(cudaMalloc(&c->d_comp, c->comp_cap + 256));
     CU(cudaMemset(c->d_in, 0, nb * kBlockBytes + 256));
     CU(cudaHostAlloc(&c->h_sub, nsb * sizeof(SubBlock), cudaHostAllocDefault));
@@ -157,11 +166,15 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaHostAlloc(&c->h_plan, nsb, cudaHostAllocDefault)); CU(cudaHostAlloc(&c->h_active, nb, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_active2, nb, cudaHostAllocDefault));
     CU(cudaHostAlloc(&c->h_outoff, nsb * sizeof(unsigned long long), cudaHostAllocDefault));
-    CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + 4) * sizeof(int), cudaHostAllocDefault));
+    CU(cudaHostAlloc(&c->h_status, (c->decsub_cap + nb + 4) * sizeof(int), cudaHostAllocDefault));
     CU(cudaMalloc(&c->d_v4c, sizeof(V4Counters)));
     CU(cudaMalloc(&c->d_lbuf, nb * kLitStride * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_lhist, nb * (size_t) kLitUnitsMax * 256 * sizeof(uint32_t)));
     CU(cudaMalloc(&c->d_ctxoff, nb * 257 * sizeof(uint32_t)));
+    CU(cudaMalloc(&c->d_mrng, nb * sizeof(MtfRange)));
+    CU(cudaHostAlloc(&c->h_mrng, nb * sizeof(MtfRange), cudaHostAllocDefault));
+    CU(cudaMalloc(&c->d_drng, nb * sizeof(DecRange)));
+    CU(cudaHostAlloc(&c->h_drng, nb * sizeof(DecRange), cudaHostAllocDefault));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(2, 1).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(4, 1).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
@@ -244,71 +257,83 @@ static inline bool incompressible(const SubBlock& s) {
 // parse does not need the carried MTF state, and needs the carried level only for the first sub-block).
 // MODE_COMPLETE: the rest, after the carried state may have been replaced (zlb_encoder_set_state); block 0 is
 // parsed again only if the carried level turned out different from the one the submit assumed.
-static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after, int mode = MODE_ALL) {
-    zlb_ctx* c = e->ctx;
+// one stream's contiguous block range inside a call
+struct EncRange {
+    int b0, b1;                    // blocks [b0, b1) of the call's block array
+    int level_in, level_out;       // current_level carried in (src/libzling.cpp:185) / after the last sub-block
+    uint8_t* st_in; uint8_t* st_out;   // MTF tables carried in / out (device, 65536 B each)
+    int first_dirty;               // first block whose ranks must be recomputed in the next pass (b1 = none)
+    unsigned long long out_off, out_len;   // where the range's framed bytes went inside d_out
+};
+
+// The pipeline over the blocks of a call: c->h_ilen[0..nb) is filled by the caller; R[0..nr) are the streams (ONE for the
+// stream API, many for the batch API).  mode MODE_ALL: the whole pipeline.  MODE_SUBMIT (nr == 1): plan + parse launch only,
+// returns without synchronising (the parse does not need the carried MTF state, and needs the carried level only for the first
+// sub-block).  MODE_COMPLETE (nr == 1): the rest, after the carried state may have been replaced (zlb_encoder_set_state);
+// block 0 is parsed again only if the carried level turned out different from the one the submit assumed.
+static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, EncRange* R, int nr, uint8_t* d_out, size_t out_cap, size_t* out_len, int mode) {
     cudaStream_t st = c->stream;
-    const int nb = (int) ((n + kBlockBytes - 1) / kBlockBytes);
     c->last_nblocks = nb;
     uint32_t launches = 0, parse_launches = 0, reparsed = 0;
     bool skip_first_parse = false;
     if (mode != MODE_COMPLETE) {
         for (int b = 0; b < nb; b++) {
-            c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
             c->h_active[b] = 1;
             // the parse predicts the level of every sub-block the host has not pinned (kV4Auto, zl_parse_v4.cuh: v4_next_level)
             memset(c->h_plan + (size_t) b * kMaxSubPerBlock, (int) kV4Auto, kMaxSubPerBlock);
         }
-        c->h_plan[0] = (uint8_t) e->cur_level;                    // current_level outlives blocks, libzling.cpp:185
+        for (int r = 0; r < nr; r++) c->h_plan[(size_t) R[r].b0 * kMaxSubPerBlock] = (uint8_t) R[r].level_in;   // current_level outlives blocks, libzling.cpp:185
         CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
-    } else if (c->h_plan[0] == (uint8_t) e->cur_level) {
+    } else if (c->h_plan[0] == (uint8_t) R[0].level_in) {
         skip_first_parse = true;                                  // the submit's guess of the carried level was right
     } else {
-        c->h_plan[0] = (uint8_t) e->cur_level;
+        c->h_plan[0] = (uint8_t) R[0].level_in;
         for (int b = 0; b < nb; b++) c->h_active[b] = b == 0;
         reparsed++;
     }
+    for (int r = 0; r < nr; r++) R[r].first_dirty = R[r].b0;
 
-    uint8_t* state_in = e->d_state[e->cur];
-    uint8_t* state_out = e->d_state[e->cur ^ 1];
     ParseArgs pa;
     pa.in = d_in; pa.ilen = c->d_ilen; pa.plan = c->d_plan; pa.active = c->d_active; pa.ring = c->d_ring; pa.hash = c->d_hash;
     pa.tok = c->d_tok; pa.lit = c->d_lit; pa.sub = c->d_sub; pa.nsub = c->d_nsub; pa.ntok = c->d_ntok; pa.nlit = c->d_nlit;
 
-    int first_dirty = 0, final_level = e->cur_level;
     float ms_parse = 0, ms_mtf = 0, ms_build = 0;
     for (int pass = 0;; pass++) {
         if (!(skip_first_parse && pass == 0)) {
-        CU(cudaMemcpyAsync(c->d_plan, c->h_plan, (size_t) nb * kMaxSubPerBlock, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(c->ev[EV_PARSE0], st));
-        zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
-        {
-            const int dmax = depth_main(e->level), lmax = depth_lazy1(e->level);
-            const V4Layout lay = v4_layout(dmax, lmax);
+            CU(cudaMemcpyAsync(c->d_plan, c->h_plan, (size_t) nb * kMaxSubPerBlock, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(c->d_active, c->h_active, nb, cudaMemcpyHostToDevice, st));
+            CU(cudaEventRecord(c->ev[EV_PARSE0], st));
+            zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
+            const V4Layout lay = v4_layout(depth_main(level), depth_lazy1(level));
             if (pass == 0) CU(cudaMemsetAsync(c->d_v4c, 0, sizeof(V4Counters), st));
-            switch (e->level) {                                  // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
-                case 0:  zl_rolz_parse_v4_kernel<2, 1><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
-                case 1:  zl_rolz_parse_v4_kernel<4, 1><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
-                case 2:  zl_rolz_parse_v4_kernel<6, 2><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
-                case 3:  zl_rolz_parse_v4_kernel<8, 3><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
-                default: zl_rolz_parse_v4_kernel<16, 4><<<nb, kV4T, lay.total, st>>>(pa, e->level, c->d_v4c); break;
+            switch (level) {                                      // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
+                case 0:  zl_rolz_parse_v4_kernel<2, 1><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
+                case 1:  zl_rolz_parse_v4_kernel<4, 1><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
+                case 2:  zl_rolz_parse_v4_kernel<6, 2><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
+                case 3:  zl_rolz_parse_v4_kernel<8, 3><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
+                default: zl_rolz_parse_v4_kernel<16, 4><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
             }
-        }
-        CU(cudaEventRecord(c->ev[EV_PARSE1], st));
-        launches += 2; parse_launches += 1;
+            CU(cudaEventRecord(c->ev[EV_PARSE1], st));
+            launches += 2; parse_launches += 1;
         }
         if (mode == MODE_SUBMIT) { CU(cudaGetLastError()); return ZLB_OK; }
+        int fd_min = nb;
+        for (int r = 0; r < nr; r++) {
+            MtfRange& m = c->h_mrng[r];
+            m.first = R[r].first_dirty; m.end = R[r].b1; m.b0 = R[r].b0; m.pad = 0; m.state_in = R[r].st_in; m.state_out = R[r].st_out;
+            if (R[r].first_dirty < fd_min) fd_min = R[r].first_dirty;
+            for (int b = R[r].b0; b < R[r].b1; b++) c->h_active2[b] = b >= R[r].first_dirty;   // blocks whose ranks change: rebuild their tables
+        }
+        CU(cudaMemcpyAsync(c->d_mrng, c->h_mrng, (size_t) nr * sizeof(MtfRange), cudaMemcpyHostToDevice, st));
         {
-            const dim3 lgrid(kLitUnitsMax / kLitWarps, nb - first_dirty);
-            zl_lit_count_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, c->d_lhist);
-            zl_lit_scan_kernel<<<nb - first_dirty, 256, 0, st>>>(c->d_nlit, first_dirty, c->d_lhist, c->d_ctxoff);
-            zl_lit_scatter_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, first_dirty, c->d_lhist, c->d_lbuf);
-            zl_mtf_ctx_kernel<<<256, 32, 0, st>>>(c->d_tok, c->d_lbuf, c->d_ctxoff, first_dirty, nb, state_in, state_out, c->d_ckpt);
-            launches += 3;
+            const dim3 lgrid(kLitUnitsMax / kLitWarps, nb - fd_min);
+            zl_lit_count_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, fd_min, c->d_lhist);
+            zl_lit_scan_kernel<<<nb - fd_min, 256, 0, st>>>(c->d_nlit, fd_min, c->d_lhist, c->d_ctxoff);
+            zl_lit_scatter_kernel<<<lgrid, kLitWarps * 32, 0, st>>>(c->d_tok, c->d_lit, c->d_nlit, fd_min, c->d_lhist, c->d_lbuf);
+            zl_mtf_ctx_kernel<<<dim3(256, nr), 32, 0, st>>>(c->d_tok, c->d_lbuf, c->d_ctxoff, c->d_mrng, c->d_ckpt);
+            launches += 4;
         }
         CU(cudaEventRecord(c->ev[EV_MTF1], st));
-        // everything from the first re-parsed block on has new MTF ranks: rebuild those tables
-        for (int b = 0; b < nb; b++) c->h_active2[b] = b >= first_dirty;
         CU(cudaMemcpyAsync(c->d_active2, c->h_active2, nb, cudaMemcpyHostToDevice, st));
         zl_huff_build_kernel<<<dim3(kMaxSubPerBlock, nb), 256, 0, st>>>(c->d_tok, c->d_sub, c->d_nsub, c->d_active2, c->d_tab);
         CU(cudaEventRecord(c->ev[EV_BUILD1], st));
@@ -317,7 +342,7 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         CU(cudaMemcpyAsync(c->h_ntok, c->d_ntok, nb * 4, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
-        launches += 2;
+        launches += 1;
         { float t; cudaEventElapsedTime(&t, c->ev[EV_PARSE0], c->ev[EV_PARSE1]); ms_parse += t;
           cudaEventElapsedTime(&t, c->ev[EV_PARSE1], c->ev[EV_MTF1]); ms_mtf += t;
           cudaEventElapsedTime(&t, c->ev[EV_MTF1], c->ev[EV_BUILD1]); ms_build += t; }
@@ -328,47 +353,54 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         // walk continues on the assumption that the compressibility of its last sub-block does not change with the
         // level (incompressible data stays incompressible), so all mispredicted blocks of a call are usually
         // re-parsed together, concurrently, in ONE extra pass.  A wrong assumption only costs another pass.
-        int cur = e->cur_level, nbad = 0, first_bad = -1;
-        bool exact = true;                                            // `cur` is the reference's value, not an assumption
-        for (int b = 0; b < nb; b++) {
-            const int ns = (int) c->h_nsub[b];
-            if (ns > kMaxSubPerBlock) return fail(ZLB_E_CUDA, "internal: sub-block table overflow");
-            c->h_active[b] = 0;
-            uint8_t* plan = c->h_plan + (size_t) b * kMaxSubPerBlock;
-            int bad_j = -1;
-            for (int j = 0; j < ns; j++) {
-                const SubBlock& sb = c->h_sub[(size_t) b * kMaxSubPerBlock + j];
-                if (bad_j < 0 && (int) sb.level != cur) {
-                    bad_j = j;
-                    plan[j] = (uint8_t) cur;
-                    for (int q = j + 1; q < kMaxSubPerBlock; q++) plan[q] = (uint8_t) kV4Auto;
-                } else if (bad_j < 0 && exact) {
-                    plan[j] = (uint8_t) sb.level;                     // verified: pin it for any later re-parse of this block
+        int nbad = 0;
+        for (int r = 0; r < nr; r++) {
+            int cur = R[r].level_in, first_bad = -1;
+            bool exact = true;                                        // `cur` is the reference's value, not an assumption
+            for (int b = R[r].b0; b < R[r].b1; b++) {
+                const int ns = (int) c->h_nsub[b];
+                if (ns > kMaxSubPerBlock) return fail(ZLB_E_CUDA, "internal: sub-block table overflow");
+                c->h_active[b] = 0;
+                uint8_t* plan = c->h_plan + (size_t) b * kMaxSubPerBlock;
+                int bad_j = -1;
+                for (int j = 0; j < ns; j++) {
+                    const SubBlock& sb = c->h_sub[(size_t) b * kMaxSubPerBlock + j];
+                    if (bad_j < 0 && (int) sb.level != cur) {
+                        bad_j = j;
+                        plan[j] = (uint8_t) cur;
+                        for (int q = j + 1; q < kMaxSubPerBlock; q++) plan[q] = (uint8_t) kV4Auto;
+                    } else if (bad_j < 0 && exact) {
+                        plan[j] = (uint8_t) sb.level;                 // verified: pin it for any later re-parse of this block
+                    }
+                    cur = incompressible(sb) ? 0 : level;
                 }
-                cur = incompressible(sb) ? 0 : e->level;
+                if (bad_j >= 0) {
+                    c->h_active[b] = 1; nbad++; reparsed++;
+                    if (first_bad < 0) first_bad = b;
+                    exact = false;                                    // everything behind rests on an assumption
+                }
             }
-            if (bad_j >= 0) {
-                c->h_active[b] = 1; nbad++; reparsed++;
-                if (first_bad < 0) first_bad = b;
-                exact = false;                                        // everything behind rests on an assumption
-            }
+            R[r].first_dirty = first_bad < 0 ? R[r].b1 : first_bad;
+            R[r].level_out = cur;
         }
-        if (nbad == 0) { final_level = cur; break; }
+        if (nbad == 0) break;
         if (pass > nb * kMaxSubPerBlock + 4) return fail(ZLB_E_CUDA, "internal: level-feedback replay did not converge");
-        first_dirty = first_bad;
     }
 
-    // layout of the framed stream: per sub-block 1 + 12 + olen bytes, one stop byte per block
+    // layout of the framed streams: per sub-block 1 + 12 + olen bytes, one stop byte per block; streams back to back
     unsigned long long off = 0, ntok = 0, nsub_total = 0;
-    for (int b = 0; b < nb; b++) {
-        for (int j = 0; j < (int) c->h_nsub[b]; j++) {
-            c->h_outoff[(size_t) b * kMaxSubPerBlock + j] = off;
-            off += 13ull + c->h_sub[(size_t) b * kMaxSubPerBlock + j].olen;
+    for (int r = 0; r < nr; r++) {
+        R[r].out_off = off;
+        for (int b = R[r].b0; b < R[r].b1; b++) {
+            for (int j = 0; j < (int) c->h_nsub[b]; j++) {
+                c->h_outoff[(size_t) b * kMaxSubPerBlock + j] = off;
+                off += 13ull + c->h_sub[(size_t) b * kMaxSubPerBlock + j].olen;
+            }
+            off += 1;
+            ntok += c->h_ntok[b]; nsub_total += c->h_nsub[b];
         }
-        off += 1;
-        ntok += c->h_ntok[b]; nsub_total += c->h_nsub[b];
+        R[r].out_len = off - R[r].out_off;
     }
-    if (nb == 0) off = 0;
     if (off > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_blocks: output buffer too small");
     if (nb > 0) {
         CU(cudaMemcpyAsync(c->d_outoff, c->h_outoff, (size_t) nb * kMaxSubPerBlock * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
@@ -379,7 +411,6 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
         launches += 1;
     }
     *out_len = (size_t) off;
-    *level_after = final_level;       // the caller commits (state ping-pong + level) once the call has succeeded
     c->stats.ms_parse = ms_parse; c->stats.ms_mtf = ms_mtf; c->stats.ms_huff_build = ms_build;
     c->stats.launches = launches; c->stats.parse_launches = parse_launches; c->stats.reparsed_blocks = reparsed;
     c->stats.tokens = ntok; c->stats.subblocks = nsub_total;
@@ -400,6 +431,20 @@ static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t*
             fprintf(stderr, "\n");
         }
     }
+    return ZLB_OK;
+}
+
+// the stream API: ONE stream, n bytes = the next blocks of it
+static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after, int mode = MODE_ALL) {
+    zlb_ctx* c = e->ctx;
+    const int nb = (int) ((n + kBlockBytes - 1) / kBlockBytes);
+    for (int b = 0; b < nb; b++) c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
+    EncRange R;
+    R.b0 = 0; R.b1 = nb; R.level_in = e->cur_level; R.level_out = e->cur_level;
+    R.st_in = e->d_state[e->cur]; R.st_out = e->d_state[e->cur ^ 1]; R.first_dirty = 0; R.out_off = R.out_len = 0;
+    const int rc = encode_ranges(c, e->level, d_in, nb, &R, 1, d_out, out_cap, out_len, mode);
+    if (rc) return rc;
+    *level_after = R.level_out;       // the caller commits (state ping-pong + level) once the call has succeeded
     return ZLB_OK;
 }
 
@@ -463,6 +508,67 @@ int zlb_encode_blocks(zlb_encoder* e, const uint8_t* in, size_t n, uint8_t* out,
     { float t = 0; if (cudaEventElapsedTime(&t, c->ev[EV_PACK1], c->ev[EV_END]) == cudaSuccess) c->stats.ms_d2h = t; cudaGetLastError(); }
     *out_len = produced;
     e->cur ^= 1; e->cur_level = level_after;
+    return ZLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ batch: many streams per call
+// Independent streams (each a whole stream: fresh MTF tables, current_level = level) share ONE pass of the pipeline: their
+// blocks are parsed side by side (one CTA per 16 MiB block: this is what fills the 148 SMs), the MTF rank pass runs one chain
+// per (context, stream), Huffman build / pack run per sub-block as always.  The bytes of every stream equal Encode() on it alone.
+int zlb_encode_batch(zlb_ctx* c, int level, zlb_stream_io* sv, int nstreams) {
+    if (!c || !sv || nstreams < 1) return fail(ZLB_E_ARG, "zlb_encode_batch: bad argument");
+    if (level < 0 || level > 4) return fail(ZLB_E_ARG, "zlb_encode_batch: level must be 0..4");
+    if (c->pending) return fail(ZLB_E_ARG, "zlb_encode_batch: a submitted range is pending on this context");
+    CU(cudaSetDevice(c->device));
+    size_t nb_total = 0;
+    for (int i = 0; i < nstreams; i++) {
+        sv[i].out_len = 0;
+        if (sv[i].n && (!sv[i].in || !sv[i].out)) return fail(ZLB_E_ARG, "zlb_encode_batch: null stream buffer");
+        nb_total += (sv[i].n + kBlockBytes - 1) / kBlockBytes;
+    }
+    if (nb_total > (size_t) c->max_blocks) return fail(ZLB_E_ARG, "zlb_encode_batch: the streams hold more than max_blocks blocks");
+    if (nb_total == 0) return ZLB_OK;
+    if (c->bstate_streams < nstreams) {                                  // initial tables (shared, read-only) + one scratch table per stream
+        cudaFree(c->d_bstate); c->d_bstate = nullptr; c->bstate_streams = 0;
+        CU(cudaMalloc(&c->d_bstate, ((size_t) nstreams + 1) * 65536));
+        c->bstate_streams = nstreams;
+        uint8_t init[65536];
+        for (int ctx = 0; ctx < 256; ctx++) memcpy(init + ctx * 256, kMtfInit, 256);          // lz.cpp:106-111
+        CU(cudaMemcpy(c->d_bstate, init, 65536, cudaMemcpyHostToDevice));
+    }
+    cudaStream_t st = c->stream;
+    std::vector<EncRange> R;
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    int b = 0;
+    for (int i = 0; i < nstreams; i++) {
+        const int nbi = (int) ((sv[i].n + kBlockBytes - 1) / kBlockBytes);
+        if (nbi == 0) continue;
+        for (int q = 0; q < nbi; q++) c->h_ilen[b + q] = (uint32_t) (q + 1 < nbi ? (size_t) kBlockBytes : sv[i].n - (size_t) q * kBlockBytes);
+        uint8_t* dst = c->d_in + (size_t) b * kBlockBytes;
+        CU(cudaMemcpyAsync(dst, sv[i].in, sv[i].n, cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(dst + sv[i].n, 0, 64, st));
+        EncRange r;
+        r.b0 = b; r.b1 = b + nbi; r.level_in = level; r.level_out = level; r.st_in = c->d_bstate; r.st_out = c->d_bstate + ((size_t) i + 1) * 65536;
+        r.first_dirty = b; r.out_off = r.out_len = 0;
+        R.push_back(r);
+        b += nbi;
+    }
+    CU(cudaEventRecord(c->ev[EV_H2D], st));
+    size_t produced = 0;
+    const int rc = encode_ranges(c, level, c->d_in, b, R.data(), (int) R.size(), c->d_out, c->out_cap, &produced, MODE_ALL);
+    if (rc) return rc;
+    size_t ri = 0;
+    for (int i = 0; i < nstreams; i++) {
+        if (sv[i].n == 0) continue;
+        const EncRange& r = R[ri++];
+        if (r.out_len > sv[i].out_cap) return fail(ZLB_E_OVERFLOW, "zlb_encode_batch: a stream's output buffer is too small");
+        CU(cudaMemcpyAsync(sv[i].out, c->d_out + r.out_off, (size_t) r.out_len, cudaMemcpyDeviceToHost, st));
+        sv[i].out_len = (size_t) r.out_len;
+    }
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    finish_stats(c, true);
     return ZLB_OK;
 }
 
@@ -801,18 +907,12 @@ void zlb_decoder_end(zlb_decoder* d) {
     delete d;
 }
 
-int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consumed, uint8_t* out, size_t out_cap, size_t* out_len) {
-    if (!d || !consumed || !out_len || (n && !in)) return fail(ZLB_E_ARG, "zlb_decode_blocks: null argument");
-    zlb_ctx* c = d->ctx;
-    if (c->pending) return fail(ZLB_E_ARG, "zlb_decode_blocks: a submitted encode range is pending on this context");
-    CU(cudaSetDevice(c->device));
-    *consumed = 0; *out_len = 0;
-    if (n == 0) return ZLB_OK;
-    // walk the container on the host (flag / BE32 x3 / payload, libzling.cpp:313-332)
-    std::vector<DecSub> subs;
+// walk the container of ONE stream on the host (flag / BE32 x3 / payload, libzling.cpp:313-332): appends a DecSub per framed
+// sub-block (payload offsets relative to comp_base + the stream's own offset), stops after max_blocks complete blocks
+static int walk_container(const uint8_t* in, size_t n, size_t comp_base, int block_base, int max_blocks, std::vector<DecSub>& subs, size_t* used, int* nblocks_out) {
     size_t at = 0;
     int nblocks = 0;
-    while (at < n && nblocks < c->max_blocks) {
+    while (at < n && nblocks < max_blocks) {
         uint32_t sym_off = 0;
         size_t p = at;
         bool closed = false;
@@ -830,7 +930,7 @@ int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consu
             if (s.olen < (uint32_t) kTableBytes || s.encpos > (uint32_t) kBlockBytes)
                 return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid block size.");
             if (p + s.olen > n) { p = n + 1; break; }
-            s.payload_off = p; s.block = (uint32_t) nblocks; s.sym_off = sym_off; s.pad = 0;
+            s.payload_off = comp_base + p; s.block = (uint32_t) (block_base + nblocks); s.sym_off = sym_off; s.pad = 0;
             if ((size_t) sym_off + s.rlen > 2 * kTokStride) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): lzdecode failed.");
             sym_off += s.rlen;
             p += s.olen;
@@ -838,24 +938,32 @@ int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consu
         }
         if (!closed) { subs.resize(first_sub); break; }          // incomplete block: leave it for the next call
         at = p; nblocks++;
-        if (subs.size() > c->decsub_cap) return fail(ZLB_E_FORMAT, "zlb_decode_blocks: too many sub-blocks in one call");
     }
-    if (nblocks == 0) return fail(ZLB_E_ARG, "zlb_decode_blocks: input holds no complete block");
-    if (at > c->comp_cap) return fail(ZLB_E_ARG, "zlb_decode_blocks: compressed input larger than the context's buffer");
+    *used = at; *nblocks_out = nblocks;
+    return ZLB_OK;
+}
+
+// decode the sub-blocks of `nr` streams (records in `subs`, ranges in c->h_drng) whose compressed bytes are already in c->d_comp
+static int decode_ranges(zlb_ctx* c, const std::vector<DecSub>& subs, int nr, int nblocks) {
     cudaStream_t st = c->stream;
     const int ns = (int) subs.size();
-    CU(cudaEventRecord(c->ev[EV_START], st));
-    CU(cudaMemcpyAsync(c->d_comp, in, at, cudaMemcpyHostToDevice, st));
+    if ((size_t) ns > c->decsub_cap) return fail(ZLB_E_FORMAT, "zlb_decode_blocks: too many sub-blocks in one call");
+    if (nr > c->decring_streams) {                                        // one 4 MiB offset ring per stream decoded concurrently
+        cudaFree(c->d_decring); c->d_decring = nullptr; c->decring_streams = 0;
+        CU(cudaMalloc(&c->d_decring, (size_t) nr * 256 * kRing * sizeof(uint32_t)));
+        c->decring_streams = nr;
+    }
     if (ns) CU(cudaMemcpyAsync(c->d_decsub, subs.data(), (size_t) ns * sizeof(DecSub), cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync(c->d_status, 0, ((size_t) ns + 4) * sizeof(int), st));
+    CU(cudaMemcpyAsync(c->d_drng, c->h_drng, (size_t) nr * sizeof(DecRange), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->d_status, 0, ((size_t) ns + (size_t) nr + 4) * sizeof(int), st));
     CU(cudaMemsetAsync(c->d_nsub, 0, (size_t) nblocks * 4, st));
     CU(cudaEventRecord(c->ev[EV_H2D], st));
     uint16_t* d_sym = reinterpret_cast<uint16_t*>(c->d_tok);
     if (ns) {
         zl_huff_decode_kernel<<<ns, 256, 65536, st>>>(c->d_comp, c->d_decsub, d_sym, c->d_status);
-        zl_rolz_decode_kernel<<<1, 32, 65536, st>>>(c->d_decsub, ns, d_sym, c->d_in, c->d_decring, d->d_state, c->d_nsub, c->d_status + ns);
+        zl_rolz_decode_kernel<<<nr, 32, 65536, st>>>(c->d_decsub, c->d_drng, d_sym, c->d_in, c->d_decring, c->d_nsub, c->d_status + ns);
     }
-    CU(cudaMemcpyAsync(c->h_status, c->d_status, ((size_t) ns + 4) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(c->h_status, c->d_status, ((size_t) ns + (size_t) nr + 4) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(c->h_nsub, c->d_nsub, (size_t) nblocks * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
@@ -864,7 +972,32 @@ int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consu
         if (c->h_status[i] == 2) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid huffman stream. (bad code2)");   // :392
         if (c->h_status[i] == 3) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): invalid huffman stream. (bad ex-bits)"); // :399
     }
-    if (c->h_status[ns] != 0) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): lzdecode failed.");                         // :407
+    for (int r = 0; r < nr; r++)
+        if (c->h_status[ns + r] != 0) return fail(ZLB_E_FORMAT, "baidu::zling::Decode(): lzdecode failed.");                 // :407
+    c->stats.launches = ns ? 2 : 0; c->stats.subblocks = (uint64_t) ns;
+    return ZLB_OK;
+}
+
+int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consumed, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!d || !consumed || !out_len || (n && !in)) return fail(ZLB_E_ARG, "zlb_decode_blocks: null argument");
+    zlb_ctx* c = d->ctx;
+    if (c->pending) return fail(ZLB_E_ARG, "zlb_decode_blocks: a submitted encode range is pending on this context");
+    CU(cudaSetDevice(c->device));
+    *consumed = 0; *out_len = 0;
+    if (n == 0) return ZLB_OK;
+    std::vector<DecSub> subs;
+    size_t at = 0;
+    int nblocks = 0;
+    int rc = walk_container(in, n, 0, 0, c->max_blocks, subs, &at, &nblocks);
+    if (rc) return rc;
+    if (nblocks == 0) return fail(ZLB_E_ARG, "zlb_decode_blocks: input holds no complete block");
+    if (at > c->comp_cap) return fail(ZLB_E_ARG, "zlb_decode_blocks: compressed input larger than the context's buffer");
+    cudaStream_t st = c->stream;
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    CU(cudaMemcpyAsync(c->d_comp, in, at, cudaMemcpyHostToDevice, st));
+    c->h_drng[0].s0 = 0; c->h_drng[0].s1 = (int) subs.size(); c->h_drng[0].state = d->d_state;
+    rc = decode_ranges(c, subs, 1, nblocks);
+    if (rc) return rc;
     size_t total = 0;
     for (int b = 0; b < nblocks; b++) total += c->h_nsub[b];
     if (total > out_cap) return fail(ZLB_E_OVERFLOW, "zlb_decode_blocks: output buffer too small");
@@ -876,8 +1009,65 @@ int zlb_decode_blocks(zlb_decoder* d, const uint8_t* in, size_t n, size_t* consu
     CU(cudaEventRecord(c->ev[EV_END], st));
     CU(cudaStreamSynchronize(st));
     finish_stats(c, false);
-    c->stats.launches = ns ? 2 : 0; c->stats.subblocks = (uint64_t) ns;
     *consumed = at; *out_len = total;
+    return ZLB_OK;
+}
+
+// batch: every `in` is a whole framed stream; one decode chain per stream runs concurrently (the way decode scales: a stream
+// is one serial chain, src/libzling_lz.cpp:318-376 + the stream-lifetime MTF tables, src/libzling_lz.h:137)
+int zlb_decode_batch(zlb_ctx* c, zlb_stream_io* sv, int nstreams) {
+    if (!c || !sv || nstreams < 1) return fail(ZLB_E_ARG, "zlb_decode_batch: bad argument");
+    if (c->pending) return fail(ZLB_E_ARG, "zlb_decode_batch: a submitted encode range is pending on this context");
+    if (nstreams > c->max_blocks) return fail(ZLB_E_ARG, "zlb_decode_batch: more streams than max_blocks");
+    CU(cudaSetDevice(c->device));
+    std::vector<DecSub> subs;
+    std::vector<int> b0(nstreams), nbv(nstreams);
+    size_t comp_at = 0;
+    int nblocks = 0, nr = 0;
+    cudaStream_t st = c->stream;
+    if (c->dstate_streams < nstreams) {
+        cudaFree(c->d_dstate); c->d_dstate = nullptr; c->dstate_streams = 0;
+        CU(cudaMalloc(&c->d_dstate, (size_t) nstreams * 65536));
+        c->dstate_streams = nstreams;
+    }
+    uint8_t init[65536];
+    for (int ctx = 0; ctx < 256; ctx++) memcpy(init + ctx * 256, kMtfInit, 256);          // lz.cpp:119-121
+    CU(cudaEventRecord(c->ev[EV_START], st));
+    for (int i = 0; i < nstreams; i++) {
+        sv[i].out_len = 0; b0[i] = nblocks; nbv[i] = 0;
+        if (sv[i].n == 0) continue;
+        if (!sv[i].in || !sv[i].out) return fail(ZLB_E_ARG, "zlb_decode_batch: null stream buffer");
+        const size_t s0 = subs.size();
+        size_t used = 0; int nbi = 0;
+        const int rc = walk_container(sv[i].in, sv[i].n, comp_at, nblocks, c->max_blocks - nblocks + 1, subs, &used, &nbi);
+        if (rc) return rc;
+        if (used != sv[i].n) return fail(nblocks + nbi > c->max_blocks ? ZLB_E_ARG : ZLB_E_FORMAT, "zlb_decode_batch: a stream is truncated, or the streams hold more than max_blocks blocks");
+        if (comp_at + used > c->comp_cap) return fail(ZLB_E_ARG, "zlb_decode_batch: compressed input larger than the context's buffer");
+        CU(cudaMemcpyAsync(c->d_comp + comp_at, sv[i].in, used, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(c->d_dstate + (size_t) nr * 65536, init, 65536, cudaMemcpyHostToDevice, st));
+        c->h_drng[nr].s0 = (int) s0; c->h_drng[nr].s1 = (int) subs.size(); c->h_drng[nr].state = c->d_dstate + (size_t) nr * 65536;
+        nr++;
+        comp_at += used; nbv[i] = nbi; nblocks += nbi;
+    }
+    if (nblocks > c->max_blocks) return fail(ZLB_E_ARG, "zlb_decode_batch: the streams hold more than max_blocks blocks");
+    if (nr == 0) return ZLB_OK;
+    CU(cudaStreamSynchronize(st));                                       // `init` is on the stack: the copies above must be done before it goes away
+    const int rc = decode_ranges(c, subs, nr, nblocks);
+    if (rc) return rc;
+    for (int i = 0; i < nstreams; i++) {
+        size_t total = 0;
+        for (int b = b0[i]; b < b0[i] + nbv[i]; b++) total += c->h_nsub[b];
+        if (total > sv[i].out_cap) return fail(ZLB_E_OVERFLOW, "zlb_decode_batch: a stream's output buffer is too small");
+        size_t w = 0;
+        for (int b = b0[i]; b < b0[i] + nbv[i]; b++) {
+            if (c->h_nsub[b]) CU(cudaMemcpyAsync(sv[i].out + w, c->d_in + (size_t) b * kBlockBytes, c->h_nsub[b], cudaMemcpyDeviceToHost, st));
+            w += c->h_nsub[b];
+        }
+        sv[i].out_len = total;
+    }
+    CU(cudaEventRecord(c->ev[EV_END], st));
+    CU(cudaStreamSynchronize(st));
+    finish_stats(c, false);
     return ZLB_OK;
 }
 

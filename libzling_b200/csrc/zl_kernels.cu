@@ -127,8 +127,14 @@ constexpr int kMtfChunk = 256;                                    // literal rec
 // grid 256 (one CTA = one warp per context).  Lane 0 walks the context's literal list of every block in stream
 // order (ZlingMTFEncoder::Encode, lz.cpp:112-117; the walk itself is mtf_walk, zl_mtf_walk.h: one dependent
 // shared-memory load per literal); all lanes prefetch the next records into shared memory and write the token words.
-__global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const uint32_t* lbuf_all, const uint32_t* ctx_off, int first_block, int nblocks,
-                                                        const uint8_t* state_in, uint8_t* state_out, uint8_t* checkpoints /* [nblocks][65536] */) {
+__global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const uint32_t* lbuf_all, const uint32_t* ctx_off, const MtfRange* ranges,
+                                                        uint8_t* checkpoints /* [nblocks][65536] */) {
+    // grid (256 contexts, streams of the call): every stream has its own tables; a stream whose blocks need no new ranks in this
+    // pass (first == end) is skipped
+    const MtfRange rg = ranges[blockIdx.y];
+    const int first_block = rg.first, nblocks = rg.end;
+    if (first_block >= nblocks) return;
+    const uint8_t* state_in = rg.state_in; uint8_t* state_out = rg.state_out;
     const int ctx = blockIdx.x, lane = threadIdx.x;
     __shared__ __align__(16) uint16_t s_S[256];           // rank -> byte | mtf_next(rank) << 8   (zl_mtf_walk.h)
     __shared__ __align__(16) uint16_t s_R[256];           // byte -> rank | mtf_next(rank) << 8
@@ -136,7 +142,9 @@ __global__ void __launch_bounds__(32) zl_mtf_ctx_kernel(uint32_t* tok_all, const
     __shared__ __align__(16) uint8_t s_out[kMtfChunk + 16];
     __shared__ __align__(16) uint8_t s_byte[2][kMtfChunk + 16];
     {
-        const uint8_t* src = (first_block == 0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
+        // the stream's first block starts from the carried state; a replay from a later block (level-feedback re-parse)
+        // from the checkpoint the previous pass left for that block
+        const uint8_t* src = (first_block == rg.b0 ? state_in : checkpoints + (size_t) first_block * 65536) + ctx * 256;
         for (int i = lane; i < 256; i += 32) {
             const uint32_t sy = src[i], nx = (uint32_t) mtf_next(i);
             s_S[i] = (uint16_t) (sy | (nx << 8));
@@ -573,12 +581,20 @@ __device__ __forceinline__ int warp_sym(const uint16_t* sym, int rlen, int i, in
 // One warp per stream; control flow is warp-uniform, lane 0 owns the scalar stores, all lanes copy matches.
 // Serial across blocks as well (the MTF tables are stream-lifetime state, src/libzling_lz.h:137).
 // result[0] = 0 ok / 4 = lz decode failed (libzling.cpp:406-408); block_len[b] = decoded bytes of block b.
-__global__ void __launch_bounds__(32) zl_rolz_decode_kernel(const DecSub* subs, int nsubs, const uint16_t* sym_all, uint8_t* out,
-                                                            uint32_t* ring, uint8_t* mtf_state, uint32_t* block_len, int* result) {
+// grid = streams of the call (DecRange per stream: its sub-block records, MTF tables, result slot); every stream has its own
+// offset ring at ring_all + stream * 256 * kRing.
+__global__ void __launch_bounds__(32) zl_rolz_decode_kernel(const DecSub* subs_all, const DecRange* ranges, const uint16_t* sym_all, uint8_t* out,
+                                                            uint32_t* ring_all, uint32_t* block_len, int* result_all) {
     extern __shared__ uint8_t s_sym[];                         // [ctx][rank] -> byte, 64 KiB
     __shared__ uint16_t s_head[256];
     __shared__ uint32_t s_mru[256];
     const int lane = threadIdx.x;
+    const DecRange rg = ranges[blockIdx.x];
+    const DecSub* subs = subs_all + rg.s0;
+    const int nsubs = rg.s1 - rg.s0;
+    uint32_t* ring = ring_all + (size_t) blockIdx.x * 256 * kRing;
+    uint8_t* mtf_state = rg.state;
+    int* result = result_all + blockIdx.x;
     {
         const uint4* src = reinterpret_cast<const uint4*>(mtf_state);
         uint4* dst = reinterpret_cast<uint4*>(s_sym);

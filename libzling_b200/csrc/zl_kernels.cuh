@@ -60,11 +60,25 @@ struct DecSub {
     uint32_t pad;
 };
 
+// one stream's sub-block records for the ROLZ decode of a call (zl_rolz_decode_kernel, grid.x = stream)
+struct DecRange {
+    int s0, s1;                // sub-block records [s0, s1) of the call's DecSub array, in stream order
+    uint8_t* state;            // 256 x 256 rank -> byte tables: carried in, written back when the stream's blocks decoded cleanly
+};
+
 // per-block strides of the device arrays (all blocks of a batch use the same stride)
 constexpr size_t kTokStride  = (size_t) kBlockBytes;                 // u32 tokens per block (worst case 1 per byte)
 constexpr size_t kLitStride  = (size_t) kBlockBytes;                 // u32 literal -> token index per block
 constexpr size_t kRingStride = (size_t) 256 * kRing;                 // u64 ring entries per block
 constexpr size_t kHashStride = (size_t) 256 * kSlots;                // u16 slot heads per block
+
+// one stream's block range for the MTF rank pass of a call (zl_mtf_ctx_kernel, grid.y = stream)
+struct MtfRange {
+    int first, end;            // blocks [first, end) get new ranks in this pass; first == end: nothing to do
+    int b0, pad;               // first block of the stream inside the call (first == b0: start from state_in, else from the checkpoint)
+    const uint8_t* state_in;   // 256 x 256 rank -> byte tables carried into the stream's first block
+    uint8_t* state_out;        // tables after the stream's last block
+};
 
 struct ParseArgs {
     const uint8_t*  in;        // block b at in + b * kBlockBytes

@@ -1278,10 +1278,9 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             __syncthreads();
             V4_TICK(15);
             if (tid == 0) { s_ph[20] += (unsigned long long) s_nq[0]; s_ph[21] += (unsigned long long) s_nq[1]; s_ph[22] += (unsigned long long) s_nq[2]; }
-            for (int i = warp; i < s_nq[2]; i += 32) {
-                const int rel = qmru[i];
-                const uint32_t v = v4_decide_word(cc, w, rel);
-                if (lane == 0) c.ndec[rel] = v;
+            {   // the word tests are many (every marked position without a match): one per THREAD, spread over the warps
+                const int qslot = lane * 32 + warp;
+                if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
             }
             __syncthreads();
             V4_TICK(19);
