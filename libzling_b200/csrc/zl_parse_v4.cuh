@@ -139,7 +139,7 @@ ZL_HD uint32_t z4_hash(uint32_t w) { return w + ((w >> 16) & 0xffu) * 137u + (w 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------------
 struct V4Layout {
     int dmax, lmax;
-    int rb, key, link, blink, pcnt, occw, mcnt, pf, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
+    int rb, key, link, blink, pcnt, occw, mcnt, pushw, pf, hdr, node, nodeq, fdec, fx, rank, mark, plit, sup, dec, ndec, occ, mbits, cnt, mru, mru2, scratch, total;
     int scratch_bytes;
 };
 // scratch is a union: SPEC uses it for the link builder's bucket tables, the rounds for the orbit / rank tables
@@ -157,6 +157,7 @@ __host__ __device__ inline V4Layout v4_layout(int dmax, int lmax) {
     L.pcnt  = take(4 * 256);
     L.occw  = take(4 * 256);
     L.mcnt  = take(4 * 256);
+    L.pushw = take(4 * 256);
     L.pf    = take(4 * kV4PfWords);
     L.hdr   = take(4 * kV4N);
     L.node  = take(4 * kV4N * dmax);
@@ -187,13 +188,14 @@ struct V4Ctx {
     uint32_t* tok; uint32_t* lit; SubBlock* sub; const uint8_t* plan; int base_level;
     // shared memory (indexed by rel = x - lo unless noted)
     uint32_t* rbw;                              // input bytes: ring of kV4R bytes viewed as words, indexed by block position
-    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* pcnt; uint32_t* occw; uint32_t* mcnt; uint32_t* pf; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
+    uint32_t* key; uint16_t* link; uint16_t* blink; uint32_t* pcnt; uint32_t* occw; uint32_t* mcnt; uint32_t* pushw; uint32_t* pf; uint32_t* hdr; uint32_t* node; uint32_t* nodeq;
     uint32_t* fdec; uint32_t* fx; uint16_t* rank; uint8_t* mark; uint8_t* plit; uint8_t* sup; uint32_t* dec; uint32_t* ndec;
     uint32_t* occ;                              // [256][kV4Words]: bit i of occ[c] <=> in[lo + i - 3] == c (a token END at lo + i pushes into context c;
                                                 // position lo + i - 2 has context c)
     // pcnt[c] = bytes of value c among in[lo - 3 .. lo + N - 2] (the set bits of occ[c]): an upper bound of the window positions
     // whose context byte is c, i.e. of the inserts this window can make into context c
     // occw[c]: bit w set <=> word w of occ[c] is not empty (w < 32);  mcnt[c] = MARKED positions whose context byte is c (per round)
+    // pushw[c] (per round): bit w set <=> a MARKED position in bitset word w pushes into context c: the only words a word-MRU scan visits
     // pf: Bloom bitmap (per round) of the (context, word) pairs pushed by the marked positions: a word test whose pair is neither
     //     in it nor in the carried MRU entry cannot hit (v4_decide_word), which spares the scan of the pushes
     uint32_t* mbits;                            // [kV4Words]: bit i <=> position lo + i is a token start
@@ -206,7 +208,7 @@ struct V4Ctx {
 };
 __host__ __device__ inline void v4_bind(V4Ctx& c, uint8_t* smem, const V4Layout& L) {
     c.rbw = (uint32_t*) (smem + L.rb); c.key = (uint32_t*) (smem + L.key); c.link = (uint16_t*) (smem + L.link);
-    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint32_t*) (smem + L.pcnt); c.occw = (uint32_t*) (smem + L.occw); c.mcnt = (uint32_t*) (smem + L.mcnt); c.pf = (uint32_t*) (smem + L.pf); c.hdr = (uint32_t*) (smem + L.hdr);
+    c.blink = (uint16_t*) (smem + L.blink); c.pcnt = (uint32_t*) (smem + L.pcnt); c.occw = (uint32_t*) (smem + L.occw); c.mcnt = (uint32_t*) (smem + L.mcnt); c.pushw = (uint32_t*) (smem + L.pushw); c.pf = (uint32_t*) (smem + L.pf); c.hdr = (uint32_t*) (smem + L.hdr);
     c.node = (uint32_t*) (smem + L.node); c.nodeq = (uint32_t*) (smem + L.nodeq); c.fdec = (uint32_t*) (smem + L.fdec);
     c.fx = (uint32_t*) (smem + L.fx); c.rank = (uint16_t*) (smem + L.rank); c.mark = smem + L.mark; c.plit = smem + L.plit;
     c.sup = smem + L.sup; c.dec = (uint32_t*) (smem + L.dec); c.ndec = (uint32_t*) (smem + L.ndec);
@@ -795,8 +797,8 @@ ZL_HD uint32_t v4_mru_state(const V4Ctx& c, const V4Win& w, int xrel, uint32_t c
         return base;
     }
 #endif
-    // words of the window that hold a byte cq at all (occw), between the first possible push and xrel, newest first
-    uint32_t words = c.occw[cq] & (0xffffffffu >> (31 - whi)) & (0xffffffffu << wlo);
+    // words of the window in which a marked position pushes into cq, between the first possible push and xrel, newest first
+    uint32_t words = c.pushw[cq] & (0xffffffffu >> (31 - whi)) & (0xffffffffu << wlo);
     int st_words = 0, st_push = 0;
     (void) st_words; (void) st_push;
     while (words) {
@@ -998,7 +1000,6 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
     __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
     __shared__ uint32_t s_dmax[4];
-    __shared__ uint32_t s_pflag[8];                                              // FINALIZE: contexts that received a word-MRU push in the window
     __shared__ int s_nq[4];                                                      // queue lengths of the decide stages
     __shared__ unsigned long long s_ph[24];                                      // phase timers (thread 0's clock between barriers)
     long long tprev = 0;
@@ -1163,7 +1164,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             for (int l = 0; l < 5; l++) { const int nx = __shfl_sync(0xffffffffu, cj[l], cj[l] & 31); cj[l + 1] = cj[l] < segend ? nx : cj[l]; }
             E[tid] = (uint16_t) cj[5];
             c.plit[tid] = 0;
-            if (tid < 256) c.mcnt[tid] = 0;
+            if (tid < 256) { c.mcnt[tid] = 0; c.pushw[tid] = 0; }
             if (tid >= 256 && tid < 256 + kV4PfWords) c.pf[tid - 256] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
             if (tid < 3) s_nq[tid] = 0;
@@ -1190,6 +1191,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 v4_push_of(c, (uint32_t) (lo + tid), &c3, &pw);
                 const uint32_t h = v4_pf_hash(c3, pw);
                 atomicOr(&c.pf[h >> 5], 1u << (h & 31u));
+                atomicOr(&c.pushw[c3], 1u << warp);
                 const int t = tid + (int) v4_dec_step(mydec);
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
                 else { s_exit = lo + t; s_lastrel = tid; }
@@ -1302,10 +1304,8 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             // per-context ranks of the marked positions -> ring slots of the pending inserts
             reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
             c.sup[tid] = 0;
-            if (tid < 8) s_pflag[tid] = 0;
             __syncthreads();
             V4_TICK(6);
-            if (marked) { const uint32_t c3 = v4_rb8(c.rbw, (uint32_t) (lo + tid) - 3u); atomicOr(&s_pflag[c3 >> 5], 1u << (c3 & 31)); }   // contexts that received a push
             const uint32_t kx = c.key[tid];
             const bool valid = !(kx & kV4KeyInvalid);
             const uint32_t ctx = v4_ctx_of(kx);
@@ -1338,13 +1338,9 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 wcnt[32 * 256 + tid] = (uint16_t) run;
             } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
             else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
-            if (warp >= 10) {                                             // carried word MRU: 22 warps share the contexts that received a push
-                for (int cq = warp - 10; cq < 256; cq += 22) {
-                    uint32_t v;
-                    if ((s_pflag[cq >> 5] >> (cq & 31)) & 1u) v = v4_mru_state(cc, w, Wn - 1, (uint32_t) cq);
-                    else v = w.rpos >= 0 ? 0u : c.mru[cq];               // no push in this window: the carried state (zeroed by a roll-over)
-                    if (lane == 0) c.mru2[cq] = v;
-                }
+            if ((tid & 3) == 3) {                                        // carried word MRU: context c on thread 4 c + 3 (8 contexts per warp);
+                const int cq = tid >> 2;                                 // pushw (last round's marks) tells which contexts received a push at all
+                c.mru2[cq] = c.pushw[cq] ? v4_mru_state(c, w, Wn - 1, (uint32_t) cq) : (w.rpos >= 0 ? 0u : c.mru[cq]);
             }
 #if defined(ZL_V4_PROFILE)
             atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);

@@ -129,7 +129,8 @@ int main(int argc, char** argv) {
             }
             for (int i = 0; i < 256; i++) c.mcnt[i] = cntw[i];
             for (int i = 0; i < kV4PfWords; i++) c.pf[i] = 0;
-            for (int rel = 0; rel < kV4W; rel++) if (c.mark[rel]) { uint32_t c3, pw; v4_push_of(c, (uint32_t) (lo + rel), &c3, &pw); const uint32_t h = v4_pf_hash(c3, pw); c.pf[h >> 5] |= 1u << (h & 31u); }
+            for (int i = 0; i < 256; i++) c.pushw[i] = 0;
+            for (int rel = 0; rel < kV4W; rel++) if (c.mark[rel]) { uint32_t c3, pw; v4_push_of(c, (uint32_t) (lo + rel), &c3, &pw); const uint32_t h = v4_pf_hash(c3, pw); c.pf[h >> 5] |= 1u << (h & 31u); c.pushw[c3] |= 1u << (rel >> 5); }
             bool changed = false;
             for (int rel = w.entry - lo; rel < wend - lo; rel++) {
                 if (marked_only && !c.mark[rel]) { c.ndec[rel] = c.dec[rel]; continue; }
