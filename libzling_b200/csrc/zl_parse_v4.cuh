@@ -403,6 +403,16 @@ ZL_HD void v4_spec_position(const V4Ctx& c, int lo, int rel) {
     c.hdr[rel] = nvis | ((dmin - 1u) << 5);
 }
 
+// MatchLazy's test against recorded node i of position zrel (lz.cpp:303-305): do the 4 bytes at offset `at` agree?  The node's
+// exact match length l against zrel (when its check byte matched) usually answers without touching global memory: the bytes
+// agree up to l and differ at l, so l >= at + 4 => yes, at <= l < at + 4 => no; only l < at (or an unknown l) needs the bytes.
+ZL_HD bool v4_lazy_node_hit(const V4Ctx& c, int zrel, int i, uint32_t at, uint32_t mine) {
+    const uint32_t l = c.node[zrel * c.dmax + i] & 511u;
+    if (l >= at + 4u) return true;
+    if (l >= at && l != 0u) return false;
+    return z4_in32(c.in, c.nodeq[zrel * c.lmax + i] + at) == mine;
+}
+
 // ---- SPEC E: the frozen decision of a main position ----------------------------------------------------------------------
 // fdec[rel] = flen(9) | fbest(9) << 9 | fslot(12) << 18: match length after the lazy veto / before it / ring slot of the best
 // node, all against G alone; fx[rel] gets the flags saying which of x, x+1, x+2 have an earlier same-key position in the window
@@ -429,7 +439,7 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
             if (tk > c.lmax) tk = c.lmax;
             const uint32_t mine = v4_rb32(c.rbw, (uint32_t) (x + which) + at);
             for (int i = 0; i < tk; i++)
-                if (z4_in32(c.in, c.nodeq[(rel + which) * c.lmax + i] + at) == mine) flen = 0;
+                if (v4_lazy_node_hit(c, rel + which, i, at, mine)) flen = 0;
         }
     }
     uint32_t fl = 0;
@@ -751,7 +761,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
             int tk = nvz < depth - vis ? nvz : depth - vis;
             if (tk > c.lmax) tk = c.lmax;
             for (int i = 0; i < tk; i++)
-                if (z4_in32(c.in, c.nodeq[relz * c.lmax + i] + at) == mine) return 0;
+                if (v4_lazy_node_hit(c, relz, i, at, mine)) return 0;
         }
     }
     *ref_out = ref;
@@ -1000,6 +1010,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
     __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
     __shared__ uint32_t s_dmax[4];
+    __shared__ int s_take[4];                                                    // next entry to take from the stage queues
     __shared__ int s_nq[4];                                                      // queue lengths of the decide stages
     __shared__ unsigned long long s_ph[24];                                      // phase timers (thread 0's clock between barriers)
     long long tprev = 0;
@@ -1019,7 +1030,6 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     uint8_t* scratch = smem_raw + L.scratch;
     uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
     uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
-    uint16_t* wcnt = reinterpret_cast<uint16_t*>(scratch + 4096);                   // FINALIZE: [33][256] marked positions per (warp, context)
     uint16_t* qhaz = reinterpret_cast<uint16_t*>(scratch + 24576);                  // ROUNDS: positions waiting for the hazard check,
     uint16_t* qgen = qhaz + kV4T;                                                   //         for the full probe on the pending view,
     uint16_t* qmru = qgen + kV4T;                                                   //         for the word-MRU test
@@ -1167,7 +1177,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             if (tid < 256) { c.mcnt[tid] = 0; c.pushw[tid] = 0; }
             if (tid >= 256 && tid < 256 + kV4PfWords) c.pf[tid - 256] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
-            if (tid < 3) s_nq[tid] = 0;
+            if (tid < 3) { s_nq[tid] = 0; s_take[tid] = 0; }
             __syncthreads();
             int cur = entry_rel;
             while ((cur >> 5) < warp && cur < Wn) cur = E[cur];
@@ -1255,33 +1265,38 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             tprev = r2;
             __syncthreads();
             V4_TICK(13);
-            // stages B, C, D: one queue entry per WARP at a time (cc.coop = 1: the 32 lanes evaluate the entry together)
-            for (int i = warp; i < s_nq[0]; i += 32) {
-                const int rel = qhaz[i];
+            // stages B + C + D without barriers between them: the warps take hazard-check entries one at a time (cc.coop = 1: the 32
+            // lanes evaluate the entry together) and run the full probe right away when the hazard holds; a warp that finds no
+            // entry left turns to the word tests stage A queued (one per lane).  Word tests queued late (positions whose probe
+            // found no match) wait for the barrier.
+            const int n_haz = s_nq[0], n_gen = s_nq[1], n_mru = s_nq[2];     // what stage A queued (stable: read behind its barrier)
+            while (true) {
+                int i = 0;
+                if (lane == 0) i = atomicAdd(&s_take[0], 1);
+                i = __shfl_sync(0xffffffffu, i, 0);
+                if (i >= n_haz + n_gen) break;
+                const int rel = i < n_haz ? qhaz[i] : qgen[i - n_haz];
                 const uint32_t fd = c.fdec[rel];
-                const bool hz = v4_hazard(cc, rel, fd, c.fx[rel], depth_lazy2(w.level));
-                if (lane == 0) {
-                    if (hz) qgen[atomicAdd(&s_nq[1], 1)] = (uint16_t) rel;
-                    else if (fd & 511u) c.ndec[rel] = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
-                    else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
-                }
-            }
-            __syncthreads();
-            V4_TICK(14);
-            for (int i = warp; i < s_nq[1]; i += 32) {
-                const int rel = qgen[i];
-                uint32_t rf = 0;
-                const uint32_t len = (uint32_t) v4_probe_general(cc, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
+                uint32_t len = fd & 511u, rf = (fd >> 18) & (kRing - 1);
+                if (i >= n_haz || v4_hazard(cc, rel, fd, c.fx[rel], depth_lazy2(w.level)))
+                    len = (uint32_t) v4_probe_general(cc, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
                 if (lane == 0) {
                     if (len) c.ndec[rel] = v4_dec_match(len, rf);
                     else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
                 }
             }
+            while (true) {
+                int i0 = 0;
+                if (lane == 0) i0 = atomicAdd(&s_take[1], 32);
+                i0 = __shfl_sync(0xffffffffu, i0, 0);
+                if (i0 >= n_mru) break;
+                if (i0 + lane < n_mru) { const int rel = qmru[i0 + lane]; c.ndec[rel] = v4_decide_word(c, w, rel); }
+            }
             __syncthreads();
-            V4_TICK(15);
-            if (tid == 0) { s_ph[20] += (unsigned long long) s_nq[0]; s_ph[21] += (unsigned long long) s_nq[1]; s_ph[22] += (unsigned long long) s_nq[2]; }
-            {   // the word tests are many (every marked position without a match): one per THREAD, spread over the warps
-                const int qslot = lane * 32 + warp;
+            V4_TICK(14);
+            if (tid == 0) { s_ph[20] += (unsigned long long) n_haz; s_ph[21] += (unsigned long long) n_gen; s_ph[22] += (unsigned long long) s_nq[2]; }
+            {   // the late word tests: one per thread, spread over the warps
+                const int qslot = n_mru + lane * 32 + warp;
                 if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
             }
             __syncthreads();
@@ -1301,21 +1316,9 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         {
             const V4Win w = s_win;
             const uint32_t d = c.dec[tid];
-            // per-context ranks of the marked positions -> ring slots of the pending inserts
-            reinterpret_cast<uint4*>(wcnt)[tid] = make_uint4(0, 0, 0, 0);          // rows 0..31: 16 KiB = 1024 x 16 B
+            // ring slot of every pending insert: per-context rank of the marked position (bitset popcount below it)
             c.sup[tid] = 0;
-            __syncthreads();
-            V4_TICK(6);
-            const uint32_t kx = c.key[tid];
-            const bool valid = !(kx & kV4KeyInvalid);
-            const uint32_t ctx = v4_ctx_of(kx);
-            uint32_t inwarp = 0;
-            {
-                const uint32_t grp = __match_any_sync(0xffffffffu, valid ? ctx : 256u + (uint32_t) lane);
-                const uint32_t mk = __ballot_sync(0xffffffffu, marked);
-                inwarp = (uint32_t) __popc(grp & mk & v4_lt_mask(lane));
-                if (valid && (grp >> lane) == 1u) wcnt[warp * 256 + ctx] = (uint16_t) __popc(grp & mk);
-            }
+            if (marked) c.rank[tid] = (uint16_t) v4_rank_live(c, tid, v4_ctx_of(c.key[tid]));
             const bool islit = marked && v4_dec_kind(d) == kV4Lit;
             const uint32_t bt = __ballot_sync(0xffffffffu, marked), bl = __ballot_sync(0xffffffffu, islit);
             const bool after = w.rpos >= 0 && lo + tid >= w.rpos;
@@ -1325,37 +1328,17 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             for (int o = 16; o > 0; o >>= 1) { sy += __shfl_xor_sync(0xffffffffu, sy, o); sya += __shfl_xor_sync(0xffffffffu, sya, o); }
             if (lane == 0) { s_wtok[warp] = __popc(bt); s_wlit[warp] = __popc(bl); s_wsym[warp] = (int) sy; s_wsya[warp] = (int) sya; }
             __syncthreads();
-            V4_TICK(7);
-#if defined(ZL_V4_PROFILE)
-            if (tid < 4) s_dmax[tid] = 0;
-            __syncthreads();
-            const uint32_t q0 = (uint32_t) clock64();
-#endif
-            if (tid < 256) {
-                uint32_t run = 0;
-                #pragma unroll 8
-                for (int w2 = 0; w2 < 32; w2++) { const uint32_t t = wcnt[w2 * 256 + tid]; wcnt[w2 * 256 + tid] = (uint16_t) run; run += t; }
-                wcnt[32 * 256 + tid] = (uint16_t) run;
-            } else if (warp == 8) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
-            else if (warp == 9) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
+            V4_TICK(6);
+            if (warp == 30) { v4_warp0_prefix(s_wtok, lane); v4_warp0_prefix(s_wlit, lane); }
+            else if (warp == 31) { v4_warp0_prefix(s_wsym, lane); v4_warp0_prefix(s_wsya, lane); }
             if ((tid & 3) == 3) {                                        // carried word MRU: context c on thread 4 c + 3 (8 contexts per warp);
                 const int cq = tid >> 2;                                 // pushw (last round's marks) tells which contexts received a push at all
                 c.mru2[cq] = c.pushw[cq] ? v4_mru_state(c, w, Wn - 1, (uint32_t) cq) : (w.rpos >= 0 ? 0u : c.mru[cq]);
             }
-#if defined(ZL_V4_PROFILE)
-            atomicMax(&s_dmax[tid < 256 ? 0 : (warp < 10 ? 1 : 2)], (uint32_t) clock64() - q0);
-            __syncthreads();
-            if (tid == 0) { s_ph[16] += s_dmax[0]; s_ph[17] += s_dmax[1]; s_ph[18] += s_dmax[2]; }
-#endif
-            __syncthreads();
-            V4_TICK(8);
-            c.rank[tid] = valid ? (uint16_t) (wcnt[warp * 256 + ctx] + inwarp) : (uint16_t) 0;
-            __syncthreads();
-            V4_TICK(9);
             uint32_t suffix = 0;
             if (marked) suffix = v4_claim_slot(c, tid);
             __syncthreads();
-            V4_TICK(10);
+            V4_TICK(7);
             if (marked) {
                 v4_apply_position(c, lo, tid, suffix);
                 const int ti = s_nt + s_wtok[warp] + __popc(bt & v4_lt_mask(lane));
@@ -1364,8 +1347,8 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (w.rpos >= 0 && lo + tid == w.rpos) s_rpos_nt = ti;
             }
             __syncthreads();
-            V4_TICK(11);
-            if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += wcnt[32 * 256 + tid]; }
+            V4_TICK(8);
+            if (tid < 256) { c.mru[tid] = c.mru2[tid]; c.cnt[tid] += c.mcnt[tid]; }   // mcnt: marked positions per context of the last round = this window's inserts
             if (tid == 0) {
                 V4Run r = s_run;
                 if (w.rpos >= 0) {                                       // sub-block full (lz.cpp:153): close it, open the next
