@@ -66,6 +66,7 @@ struct zlb_ctx {
     const void* pending = nullptr;  // encoder with a submitted, not yet completed range: it owns the context's buffers
     V4Counters* d_v4c = nullptr;
     V4Counters  h_v4c = {};
+    int parse_cluster = 0;          // CTAs per block of the parse kernel; 0 = choose by the number of blocks (ZLB_PARSE_CLUSTER=1|2|4 pins it)
     uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
     MtfRange *d_mrng = nullptr, *h_mrng = nullptr;   // per-stream block ranges of the MTF pass (max_blocks entries)
     uint8_t* d_bstate = nullptr;                     // batch API: initial MTF tables + one scratch table per stream, allocated on first use
@@ -180,6 +181,7 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(8, 3).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(16, 4).total));
+    { const char* pv = getenv("ZLB_PARSE_CLUSTER"); if (pv && (*pv == '1' || *pv == '2' || *pv == '4') && !pv[1]) c->parse_cluster = *pv - '0'; }
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     return ZLB_OK;
@@ -306,12 +308,24 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
             zl_reset_buckets_kernel<<<296, 256, 0, st>>>(c->d_ring, c->d_hash, c->d_active, nb);
             const V4Layout lay = v4_layout(depth_main(level), depth_lazy1(level));
             if (pass == 0) CU(cudaMemsetAsync(c->d_v4c, 0, sizeof(V4Counters), st));
-            switch (level) {                                      // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
-                case 0:  zl_rolz_parse_v4_kernel<2, 1><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
-                case 1:  zl_rolz_parse_v4_kernel<4, 1><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
-                case 2:  zl_rolz_parse_v4_kernel<6, 2><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
-                case 3:  zl_rolz_parse_v4_kernel<8, 3><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
-                default: zl_rolz_parse_v4_kernel<16, 4><<<nb, kV4T, lay.total, st>>>(pa, level, c->d_v4c); break;
+            {
+                // one CTA per block, or a cluster of CTAs per block (helpers take the chain walks, zl_parse_v4.cuh) while the clusters
+                // of all blocks of the call still fit the GPU at once
+                int cl = c->parse_cluster;
+                if (cl <= 0) cl = nb * 4 <= 120 ? 4 : (nb * 2 <= 120 ? 2 : 1);
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned) (nb * cl)); cfg.blockDim = dim3(kV4T); cfg.dynamicSmemBytes = (size_t) lay.total; cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = (unsigned) cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                switch (level) {                                  // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
+                    case 0:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<2, 1>, pa, level, c->d_v4c)); break;
+                    case 1:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<4, 1>, pa, level, c->d_v4c)); break;
+                    case 2:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<6, 2>, pa, level, c->d_v4c)); break;
+                    case 3:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<8, 3>, pa, level, c->d_v4c)); break;
+                    default: CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<16, 4>, pa, level, c->d_v4c)); break;
+                }
             }
             CU(cudaEventRecord(c->ev[EV_PARSE1], st));
             launches += 2; parse_launches += 1;

@@ -981,7 +981,9 @@ ZL_HD void v4_resolve_tail(const V4Ctx& c, V4Run& r, int* nt_io, int* nl_io) {
 }  // namespace zl
 
 #if defined(__CUDACC__)
+#include <cooperative_groups.h>
 namespace zl {
+namespace cg = cooperative_groups;
 
 struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[24]; };
 
@@ -1002,7 +1004,12 @@ __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
 template <int DMAX, int LMAX>
 __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, int base_level, V4Counters* counters) {
     constexpr int dmax = DMAX, lmax = LMAX;
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // A block may be given a thread-block CLUSTER of CL CTAs (launch attribute): CTA 0 of the cluster (the leader) runs the
+    // pipeline below; the other CTAs (helpers, each on its own SM) do the one part that is pure throughput — the chain walk of
+    // every position against G — and write the records straight into the leader's shared memory (DSMEM).  CL = 1: no helpers.
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int) cluster.num_blocks(), crank = (int) cluster.block_rank();
+    const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!a.active[b]) return;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ V4Run s_run;
@@ -1025,6 +1032,39 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     c.tok = a.tok + (size_t) b * kTokStride; c.lit = a.lit + (size_t) b * kLitStride;
     c.sub = a.sub + (size_t) b * kMaxSubPerBlock; c.plan = a.plan + (size_t) b * kMaxSubPerBlock; c.base_level = base_level;
     const int ilen = c.ilen;
+    if (crank != 0) {
+        // ---------------------------------------------------------------- helper CTA: SPEC D for a share of the positions
+        __shared__ int s_hip;
+        V4Ctx hc = c;                                                    // own byte ring + own key array; counters and records are the leader's
+        hc.cnt = cluster.map_shared_rank(c.cnt, 0);
+        hc.hdr = cluster.map_shared_rank(c.hdr, 0); hc.node = cluster.map_shared_rank(c.node, 0);
+        hc.nodeq = cluster.map_shared_rank(c.nodeq, 0); hc.fx = cluster.map_shared_rank(c.fx, 0);
+        const int* leader_ip = &cluster.map_shared_rank(&s_run, 0)->ip;
+        const int H = CL - 1, chunk = (kV4N + H - 1) / H;
+        const int r0 = (crank - 1) * chunk, r1 = r0 + chunk < kV4N ? r0 + chunk : kV4N;
+        const int hlim = ilen - kGuard;
+        const int hnwin = hlim > 2 ? (hlim + kV4W - 1) / kV4W : 0;
+        int hstaged = -16;
+        for (int k = 0; k < hnwin; k++) {
+            const int lo = k * kV4W;
+            const int wend = lo + kV4W < hlim ? lo + kV4W : hlim;
+            const int hi = v4_stage_hi(k);
+            for (int src = hstaged + tid * 16; src < hi; src += kV4T * 16) v4_stage16(c, src);
+            hstaged = hi;
+            __syncthreads();
+            cluster.sync();                                              // B1: the leader has finished the previous window (G, counters, run state)
+            if (tid == 0) s_hip = *leader_ip;
+            __syncthreads();
+            if (s_hip >= wend) continue;                                 // the leader skips this window too
+            const int rel = r0 + tid;
+            if (rel < r1) {
+                c.key[rel] = v4_key_of(c, lo + rel);
+                v4_spec_position(hc, lo, rel);
+            }
+            cluster.sync();                                              // B2: the records are in the leader's shared memory
+        }
+        return;
+    }
     V4Ctx cc = c;                                                        // the same state, evaluated by a whole warp per position
     cc.coop = 1;
     uint8_t* scratch = smem_raw + L.scratch;
@@ -1090,6 +1130,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         for (int src = staged_hi + tid * 16; src < hi; src += kV4T * 16) v4_stage16(c, src);
         staged_hi = hi;
         __syncthreads();
+        if (CL > 1) cluster.sync();                                      // B1 (see the helper loop above)
         if (s_run.ip >= wend) continue;                                  // no token starts in this window (uniform)
         const long long t0 = clock64();
         tprev = t0;
@@ -1107,7 +1148,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             if (p >= 0 && (grp >> lane) == 1u) { c.occ[v * kV4Words + warp] = grp; atomicAdd(&c.pcnt[v], (uint32_t) __popc(grp)); atomicOr(&c.occw[v], 1u << warp); }
             if (tid < 2) { const int p2 = lo + kV4N + tid - 3; const uint32_t v2 = v4_rb8(c.rbw, (uint32_t) p2); atomicOr(&c.occ[v2 * kV4Words + (kV4N >> 5)], 1u << tid); atomicAdd(&c.pcnt[v2], 1u); }
         }
-        v4_spec_position(c, lo, tid);                                    // chain records against G (global-memory latency lives here)
+        if (CL == 1) v4_spec_position(c, lo, tid);                       // chain records against G (with a cluster: done by the helper CTAs)
         V4_TICK(1);
         {   // link builder: nearest earlier position of the window in the same bucket.  Groups of 4 warps own a bucket table;
             // inside a group the warps take turns in position order, then positions without a predecessor in their own
@@ -1145,6 +1186,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         V4_TICK(3);
         v4_link_position(c, tid);
         __syncthreads();
+        if (CL > 1) cluster.sync();                                      // B2: the helpers' records have arrived
         V4_TICK(4);
         const int wlevel = s_run.level;
         if (tid < kV4W) v4_frozen_position(c, lo, tid, wlevel);

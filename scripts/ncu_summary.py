@@ -38,7 +38,7 @@ with open(out, "w", newline="") as f:
     w.writerow(["kernel", "duration_ms", "dram_read_bytes", "dram_write_bytes"] + want[4:])
     seen = set()
     for r in data:
-        name = r[col["Kernel Name"]].split("(")[0].replace("zl::", "")
+        name = r[col["Kernel Name"]].split("(")[0].replace("zl::", "").replace("void ", "")
         dur = scale(r[col["gpu__time_duration.sum"]], units[col["gpu__time_duration.sum"]])
         rd = scale(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
         wr = scale(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
