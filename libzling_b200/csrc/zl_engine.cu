@@ -66,7 +66,7 @@ struct zlb_ctx {
     const void* pending = nullptr;  // encoder with a submitted, not yet completed range: it owns the context's buffers
     V4Counters* d_v4c = nullptr;
     V4Counters  h_v4c = {};
-    int parse_cluster = 0;          // CTAs per block of the parse kernel; 0 = choose by the number of blocks (ZLB_PARSE_CLUSTER=1|2|4 pins it)
+    int parse_cluster = 0;          // CTAs per block of the parse kernel; 0 = choose by the number of blocks (ZLB_PARSE_CLUSTER=1|2|4|8 pins it)
     uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
     MtfRange *d_mrng = nullptr, *h_mrng = nullptr;   // per-stream block ranges of the MTF pass (max_blocks entries)
     uint8_t* d_bstate = nullptr;                     // batch API: initial MTF tables + one scratch table per stream, allocated on first use
@@ -181,7 +181,7 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(8, 3).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(16, 4).total));
-    { const char* pv = getenv("ZLB_PARSE_CLUSTER"); if (pv && (*pv == '1' || *pv == '2' || *pv == '4') && !pv[1]) c->parse_cluster = *pv - '0'; }
+    { const char* pv = getenv("ZLB_PARSE_CLUSTER"); if (pv && (*pv == '1' || *pv == '2' || *pv == '4' || *pv == '8') && !pv[1]) c->parse_cluster = *pv - '0'; }
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     return ZLB_OK;
@@ -312,7 +312,7 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
                 // one CTA per block, or a cluster of CTAs per block (helpers take the chain walks, zl_parse_v4.cuh) while the clusters
                 // of all blocks of the call still fit the GPU at once
                 int cl = c->parse_cluster;
-                if (cl <= 0) cl = nb * 4 <= 120 ? 4 : (nb * 2 <= 120 ? 2 : 1);
+                if (cl <= 0) cl = nb * 8 <= 120 ? 8 : (nb * 4 <= 120 ? 4 : (nb * 2 <= 120 ? 2 : 1));
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3((unsigned) (nb * cl)); cfg.blockDim = dim3(kV4T); cfg.dynamicSmemBytes = (size_t) lay.total; cfg.stream = st;
                 cudaLaunchAttribute attr[1];

@@ -416,7 +416,8 @@ ZL_HD bool v4_lazy_node_hit(const V4Ctx& c, int zrel, int i, uint32_t at, uint32
 // ---- SPEC E: the frozen decision of a main position ----------------------------------------------------------------------
 // fdec[rel] = flen(9) | fbest(9) << 9 | fslot(12) << 18: match length after the lazy veto / before it / ring slot of the best
 // node, all against G alone; fx[rel] gets the flags saying which of x, x+1, x+2 have an earlier same-key position in the window
-ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
+// part 1 (needs only the records: the helper CTAs of a cluster run it): fdec
+ZL_HD void v4_frozen_core(const V4Ctx& c, int lo, int rel, int level) {
     const int x = lo + rel;
     const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
     const uint32_t hdr = c.hdr[rel];
@@ -429,8 +430,7 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
     }
     uint32_t flen = fbest >= (uint32_t) kMinLen ? fbest : 0u;
     if (fbest < (uint32_t) kMinLen) fbest = 0;
-    const bool lazy_matters = fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow;
-    if (lazy_matters) {                                                  // lz.cpp:270-281 against G
+    if (fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow) {  // lz.cpp:270-281 against G
         const uint32_t at = fbest - 3u;
         for (int which = 1; which <= 2 && flen; which++) {
             const int depth = which == 1 ? L1 : L2;
@@ -442,6 +442,14 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
                 if (v4_lazy_node_hit(c, rel + which, i, at, mine)) flen = 0;
         }
     }
+    c.fdec[rel] = flen | (fbest << 9) | (fslot << 18);
+}
+// part 2 (needs the window's links and byte counts): the flags of fx
+ZL_HD void v4_frozen_flags(const V4Ctx& c, int rel) {
+    const uint32_t hdr = c.hdr[rel];
+    const int nvis = (int) (hdr & 31u);
+    const uint32_t fbest = (c.fdec[rel] >> 9) & 511u;
+    const bool lazy_matters = fbest >= (uint32_t) kMinLen && fbest < (uint32_t) kLazyBelow;
     uint32_t fl = 0;
     if (c.link[rel]) fl |= kV4F_SELF;
     if (lazy_matters) {
@@ -459,8 +467,11 @@ ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
         }
         if (st) fl |= kV4F_ST;
     }
-    c.fdec[rel] = flen | (fbest << 9) | (fslot << 18);
     c.fx[rel] = (c.fx[rel] & 0xffffu) | fl;
+}
+ZL_HD void v4_frozen_position(const V4Ctx& c, int lo, int rel, int level) {
+    v4_frozen_core(c, lo, rel, level);
+    v4_frozen_flags(c, rel);
 }
 
 // ---- ROUNDS: the pending view -----------------------------------------------------------------------------------------------
@@ -1034,14 +1045,16 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     const int ilen = c.ilen;
     if (crank != 0) {
         // ---------------------------------------------------------------- helper CTA: SPEC D for a share of the positions
-        __shared__ int s_hip;
-        V4Ctx hc = c;                                                    // own byte ring + own key array; counters and records are the leader's
+        __shared__ int s_hip, s_hlevel;
+        V4Ctx hc = c;                                                    // own byte ring, own copy of the records; the insert counters are the leader's
         hc.cnt = cluster.map_shared_rank(c.cnt, 0);
-        hc.hdr = cluster.map_shared_rank(c.hdr, 0); hc.node = cluster.map_shared_rank(c.node, 0);
-        hc.nodeq = cluster.map_shared_rank(c.nodeq, 0); hc.fx = cluster.map_shared_rank(c.fx, 0);
-        const int* leader_ip = &cluster.map_shared_rank(&s_run, 0)->ip;
+        uint32_t* l_hdr = cluster.map_shared_rank(c.hdr, 0); uint32_t* l_node = cluster.map_shared_rank(c.node, 0);
+        uint32_t* l_nodeq = cluster.map_shared_rank(c.nodeq, 0); uint32_t* l_fx = cluster.map_shared_rank(c.fx, 0);
+        uint32_t* l_fdec = cluster.map_shared_rank(c.fdec, 0);
+        const V4Run* leader_run = cluster.map_shared_rank(&s_run, 0);
         const int H = CL - 1, chunk = (kV4N + H - 1) / H;
         const int r0 = (crank - 1) * chunk, r1 = r0 + chunk < kV4N ? r0 + chunk : kV4N;
+        const int r2 = r1 + 2 < kV4N ? r1 + 2 : kV4N;                    // two more records: the lazy tests of the last positions look at them
         const int hlim = ilen - kGuard;
         const int hnwin = hlim > 2 ? (hlim + kV4W - 1) / kV4W : 0;
         int hstaged = -16;
@@ -1053,15 +1066,24 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             hstaged = hi;
             __syncthreads();
             cluster.sync();                                              // B1: the leader has finished the previous window (G, counters, run state)
-            if (tid == 0) s_hip = *leader_ip;
+            if (tid == 0) { s_hip = leader_run->ip; s_hlevel = leader_run->level; }
             __syncthreads();
             if (s_hip >= wend) continue;                                 // the leader skips this window too
             const int rel = r0 + tid;
-            if (rel < r1) {
+            if (rel < r2) {
                 c.key[rel] = v4_key_of(c, lo + rel);
                 v4_spec_position(hc, lo, rel);
             }
-            cluster.sync();                                              // B2: the records are in the leader's shared memory
+            __syncthreads();
+            if (rel < r1) {
+                if (rel < kV4W) { v4_frozen_core(c, lo, rel, s_hlevel); l_fdec[rel] = c.fdec[rel]; }
+                l_hdr[rel] = c.hdr[rel]; l_fx[rel] = c.fx[rel];
+                #pragma unroll
+                for (int i = 0; i < DMAX; i++) l_node[rel * DMAX + i] = c.node[rel * DMAX + i];
+                #pragma unroll
+                for (int i = 0; i < LMAX; i++) l_nodeq[rel * LMAX + i] = c.nodeq[rel * LMAX + i];
+            }
+            cluster.sync();                                              // B2: records and frozen decisions are in the leader's shared memory
         }
         return;
     }
@@ -1189,7 +1211,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         if (CL > 1) cluster.sync();                                      // B2: the helpers' records have arrived
         V4_TICK(4);
         const int wlevel = s_run.level;
-        if (tid < kV4W) v4_frozen_position(c, lo, tid, wlevel);
+        if (tid < kV4W) { if (CL == 1) v4_frozen_core(c, lo, tid, wlevel); v4_frozen_flags(c, tid); }
         if (tid == 0) {
             V4Win w; w.lo = lo; w.wend = wend; w.entry = s_run.ip; w.level = wlevel; w.rpos = -1; w.level2 = wlevel;
             w.skip_push = s_run.skip_push; w.prev_lit = s_run.prev_lit;
