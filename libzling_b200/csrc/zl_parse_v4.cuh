@@ -1077,11 +1077,11 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             __syncthreads();
             if (rel < r1) {
                 if (rel < kV4W) { v4_frozen_core(c, lo, rel, s_hlevel); l_fdec[rel] = c.fdec[rel]; }
-                l_hdr[rel] = c.hdr[rel]; l_fx[rel] = c.fx[rel];
-                #pragma unroll
-                for (int i = 0; i < DMAX; i++) l_node[rel * DMAX + i] = c.node[rel * DMAX + i];
-                #pragma unroll
-                for (int i = 0; i < LMAX; i++) l_nodeq[rel * LMAX + i] = c.nodeq[rel * LMAX + i];
+                const uint32_t hd = c.hdr[rel];
+                const int nv = (int) (hd & 31u);                          // only the recorded nodes travel
+                l_hdr[rel] = hd; l_fx[rel] = c.fx[rel];
+                for (int i = 0; i < nv; i++) l_node[rel * DMAX + i] = c.node[rel * DMAX + i];
+                for (int i = 0; i < nv && i < LMAX; i++) l_nodeq[rel * LMAX + i] = c.nodeq[rel * LMAX + i];
             }
             cluster.sync();                                              // B2: records and frozen decisions are in the leader's shared memory
         }
@@ -1181,14 +1181,12 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             const bool valid = !(kx & kV4KeyInvalid);
             const uint32_t bk = valid ? v4_bucket_of(kx) : 0xffff0000u + (uint32_t) lane;
             uint32_t dist = 0;
+            const uint32_t grp = __match_any_sync(0xffffffffu, bk);      // same-bucket lanes of this warp (all warps at once; only the
+            const uint32_t lower = grp & v4_lt_mask(lane);               // table look-ups below have to go in position order)
+            if (valid && lower) dist = (uint32_t) lane - (31u - (uint32_t) __clz(lower));
             for (int i = 0; i < 4; i++) {
                 if (turn == i) {
-                    const uint32_t grp = __match_any_sync(0xffffffffu, bk);
-                    const uint32_t lower = grp & v4_lt_mask(lane);
-                    if (valid) {
-                        if (lower) dist = (uint32_t) lane - (31u - (uint32_t) __clz(lower));
-                        else { const uint32_t prev = tg[bk]; if (prev) dist = (uint32_t) tid - (prev - 1u); }
-                    }
+                    if (valid && !lower) { const uint32_t prev = tg[bk]; if (prev) dist = (uint32_t) tid - (prev - 1u); }
                     __syncwarp();
                     if (valid && (grp >> lane) == 1u) tg[bk] = (uint16_t) (tid + 1);
                 }
