@@ -403,6 +403,42 @@ ZL_HD void v4_spec_position(const V4Ctx& c, int lo, int rel) {
     c.hdr[rel] = nvis | ((dmin - 1u) << 5);
 }
 
+// The same record in two steps, for helper CTAs that have more threads than positions: the chain walk (dependent ring loads, one
+// thread per position) leaves every candidate position in qall[rel * dmax + i] (bit 31: its check byte matches), the compares
+// (the bulk of the work at the deep levels) are then spread over several threads per position.
+ZL_HD void v4_spec_walk(const V4Ctx& c, int lo, int rel, uint32_t* qall) {
+    const uint32_t k = c.key[rel];
+    if (k & kV4KeyInvalid) { c.hdr[rel] = (uint32_t) (kRing - 1) << 5; c.fx[rel] = (uint32_t) kNil; return; }
+    const uint32_t ctx = v4_ctx_of(k), slot = k & (kSlots - 1), chk = k >> 21;
+    const uint32_t head_b = c.cnt[ctx] & (kRing - 1);
+    const uint64_t* rc = c.ring + (size_t) ctx * kRing;
+    uint32_t node = z4_ld_hash(c.hash + (size_t) ctx * kSlots + slot);
+    c.fx[rel] = node;
+    uint32_t nvis = 0, dmin = kRing;
+    if (node != (uint32_t) kNil) {
+        dmin = v4_ring_dist(node, head_b);
+        uint64_t e = z4_ld_ring(rc + node);
+        for (int i = 0; i < c.dmax; i++) {
+            const uint32_t q = ring_pos(e);
+            const uint32_t nxt = ring_suffix(e);
+            const uint64_t e2 = nxt != (uint32_t) kNil ? z4_ld_ring(rc + nxt) : 0ull;
+            c.node[rel * c.dmax + i] = node << 9;
+            qall[rel * c.dmax + i] = q | (ring_check(e) == chk ? 0x80000000u : 0u);
+            if (i < c.lmax) c.nodeq[rel * c.lmax + i] = q;
+            nvis = i + 1;
+            if (nxt == (uint32_t) kNil) break;
+            dmin = min(dmin, v4_ring_dist(nxt, head_b));
+            if (q <= ring_pos(e2)) break;                                // lz.cpp:264
+            node = nxt; e = e2;
+        }
+    }
+    c.hdr[rel] = nvis | ((dmin - 1u) << 5);
+}
+ZL_HD void v4_spec_compare(const V4Ctx& c, int lo, int rel, int i, const uint32_t* qall) {
+    const uint32_t v = qall[rel * c.dmax + i];
+    if (v >> 31) c.node[rel * c.dmax + i] |= (uint32_t) v4_common_len_mixed(c, (uint32_t) (lo + rel), v & 0xffffffu);
+}
+
 // MatchLazy's test against recorded node i of position zrel (lz.cpp:303-305): do the 4 bytes at offset `at` agree?  The node's
 // exact match length l against zrel (when its check byte matched) usually answers without touching global memory: the bytes
 // agree up to l and differ at l, so l >= at + 4 => yes, at <= l < at + 4 => no; only l < at (or an unknown l) needs the bytes.
@@ -1055,6 +1091,8 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         const int H = CL - 1, chunk = (kV4N + H - 1) / H;
         const int r0 = (crank - 1) * chunk, r1 = r0 + chunk < kV4N ? r0 + chunk : kV4N;
         const int r2 = r1 + 2 < kV4N ? r1 + 2 : kV4N;                    // two more records: the lazy tests of the last positions look at them
+        const int T = kV4T / (r2 - r0) < 1 ? 1 : (kV4T / (r2 - r0) > DMAX ? DMAX : kV4T / (r2 - r0));   // threads per position in the compare step
+        uint32_t* qall = reinterpret_cast<uint32_t*>(smem_raw + L.scratch);   // [kV4N * DMAX] candidate positions (the helpers do not use the scratch area otherwise)
         const int hlim = ilen - kGuard;
         const int hnwin = hlim > 2 ? (hlim + kV4W - 1) / kV4W : 0;
         int hstaged = -16;
@@ -1072,7 +1110,15 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             const int rel = r0 + tid;
             if (rel < r2) {
                 c.key[rel] = v4_key_of(c, lo + rel);
-                v4_spec_position(hc, lo, rel);
+                v4_spec_walk(hc, lo, rel, qall);
+            }
+            __syncthreads();
+            {   // compares: T threads per position, each takes every T-th recorded node
+                const int prel = r0 + tid / T, sub = tid % T;
+                if (prel < r2) {
+                    const int nv = (int) (c.hdr[prel] & 31u);
+                    for (int i = sub; i < nv; i += T) v4_spec_compare(c, lo, prel, i, qall);
+                }
             }
             __syncthreads();
             if (rel < r1) {
