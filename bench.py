@@ -239,11 +239,11 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if "NCCL_DEBUG" not in os.environ:           # keep NCCL's INFO log (communicator sizes, transports) but off stdout:
+        if "NCCL_DEBUG_FILE" not in os.environ:      # keep NCCL's INFO log (communicator sizes, transports) but off stdout:
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)     # rank 0 prints exactly one JSON line there
             os.environ["NCCL_DEBUG"] = "INFO"
-            os.environ["NCCL_DEBUG_SUBSYS"] = "INIT"
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_n%d_%%h_%%p.log" % world)
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_n%d_rank%d.log" % (world, rank))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     if args.mode == "decode":

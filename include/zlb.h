@@ -134,6 +134,7 @@ typedef struct {
     double   ms_gather;       /* sizes + payload gather (+ D2H of the whole stream on rank 0) */
     uint64_t local_bytes;     /* framed bytes of this rank's range */
     uint64_t total_bytes;     /* framed bytes of the whole stream */
+    uint64_t spec_reparsed_blocks; /* blocks re-parsed for the level feedback before the carried state arrived (ranks > 0) */
 } zlb_shard_stats;
 int       zlb_comm_get_unique_id(uint8_t* id /* ZLB_COMM_ID_BYTES */);
 zlb_comm* zlb_comm_create(zlb_ctx* ctx, int rank, int world, const uint8_t* id /* ZLB_COMM_ID_BYTES */);

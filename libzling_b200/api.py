@@ -33,7 +33,7 @@ class Stats(C.Structure):
 
 
 class ShardStats(C.Structure):
-    _fields_ = [("ms_wait_carry", C.c_double), ("ms_gather", C.c_double), ("local_bytes", C.c_uint64), ("total_bytes", C.c_uint64)]
+    _fields_ = [("ms_wait_carry", C.c_double), ("ms_gather", C.c_double), ("local_bytes", C.c_uint64), ("total_bytes", C.c_uint64), ("spec_reparsed_blocks", C.c_uint64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

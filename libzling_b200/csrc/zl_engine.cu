@@ -36,6 +36,7 @@ enum { EV_START, EV_H2D, EV_PARSE0, EV_PARSE1, EV_MTF1, EV_BUILD1, EV_PACK0, EV_
 
 struct zlb_ctx {
     int device = 0, max_blocks = 0;
+    uint32_t spec_reparsed = 0;     // blocks re-parsed by the last speculative completion (sharded streams)
     cudaStream_t stream = nullptr;
     // device
     uint8_t*  d_in = nullptr;       // max_blocks * 16 MiB + pad (host-input path)
@@ -83,7 +84,7 @@ struct zlb_encoder {
     int cur;
     size_t submitted_n;      // bytes handed to zlb_encode_submit and not yet completed (0 = nothing pending)
 };
-enum { MODE_ALL = 0, MODE_SUBMIT = 1, MODE_COMPLETE = 2 };
+enum { MODE_ALL = 0, MODE_SUBMIT = 1, MODE_COMPLETE = 2, MODE_SPECULATE = 3 };
 struct zlb_decoder {
     zlb_ctx* ctx;
     uint8_t* d_state;
@@ -273,23 +274,30 @@ struct EncRange {
 // returns without synchronising (the parse does not need the carried MTF state, and needs the carried level only for the first
 // sub-block).  MODE_COMPLETE (nr == 1): the rest, after the carried state may have been replaced (zlb_encoder_set_state);
 // block 0 is parsed again only if the carried level turned out different from the one the submit assumed.
-static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, EncRange* R, int nr, uint8_t* d_out, size_t out_cap, size_t* out_len, int mode) {
+static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, EncRange* R, int nr, uint8_t* d_out, size_t out_cap, size_t* out_len, int mode, const uint8_t* pre_tail = nullptr) {
     cudaStream_t st = c->stream;
     c->last_nblocks = nb;
     uint32_t launches = 0, parse_launches = 0, reparsed = 0;
     bool skip_first_parse = false;
-    if (mode != MODE_COMPLETE) {
+    if (mode == MODE_SPECULATE) {
+        skip_first_parse = true;                                  // the submitted parse is the first pass
+    } else if (mode != MODE_COMPLETE) {
         for (int b = 0; b < nb; b++) {
             c->h_active[b] = 1;
             // the parse predicts the level of every sub-block the host has not pinned (kV4Auto, zl_parse_v4.cuh: v4_next_level)
             memset(c->h_plan + (size_t) b * kMaxSubPerBlock, (int) kV4Auto, kMaxSubPerBlock);
         }
         for (int r = 0; r < nr; r++) c->h_plan[(size_t) R[r].b0 * kMaxSubPerBlock] = (uint8_t) R[r].level_in;   // current_level outlives blocks, libzling.cpp:185
+        // a range of a sharded stream whose carried level is still on its way: the kernel predicts it from the bytes that precede
+        // the range (pre_tail), the walk below verifies it against the carried level like every other prediction
+        if (pre_tail && nr == 1 && nb > 0) c->h_plan[(size_t) R[0].b0 * kMaxSubPerBlock] = (uint8_t) kV4Auto;
         CU(cudaMemcpyAsync(c->d_ilen, c->h_ilen, nb * 4, cudaMemcpyHostToDevice, st));
-    } else if (c->h_plan[0] == (uint8_t) R[0].level_in) {
-        skip_first_parse = true;                                  // the submit's guess of the carried level was right
+    } else if (c->h_plan[0] == (uint8_t) R[0].level_in || c->h_plan[0] == (uint8_t) kV4Auto) {
+        skip_first_parse = true;                                  // the submit's guess of the carried level was right (or the kernel's
+                                                                  // own prediction is verified by the walk below)
     } else {
         c->h_plan[0] = (uint8_t) R[0].level_in;
+        memset(c->h_plan + 1, (int) kV4Auto, kMaxSubPerBlock - 1);  // levels pinned by a speculative completion rested on the wrong start
         for (int b = 0; b < nb; b++) c->h_active[b] = b == 0;
         reparsed++;
     }
@@ -298,6 +306,7 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
     ParseArgs pa;
     pa.in = d_in; pa.ilen = c->d_ilen; pa.plan = c->d_plan; pa.active = c->d_active; pa.ring = c->d_ring; pa.hash = c->d_hash;
     pa.tok = c->d_tok; pa.lit = c->d_lit; pa.sub = c->d_sub; pa.nsub = c->d_nsub; pa.ntok = c->d_ntok; pa.nlit = c->d_nlit;
+    pa.pre_tail = pre_tail;
 
     float ms_parse = 0, ms_mtf = 0, ms_build = 0;
     for (int pass = 0;; pass++) {
@@ -370,6 +379,8 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
         int nbad = 0;
         for (int r = 0; r < nr; r++) {
             int cur = R[r].level_in, first_bad = -1;
+            // MODE_SPECULATE: the carried level is not known yet; trust the one the parse predicted for the range's first sub-block
+            if (mode == MODE_SPECULATE && R[r].b0 < R[r].b1 && c->h_nsub[R[r].b0] > 0) cur = (int) c->h_sub[(size_t) R[r].b0 * kMaxSubPerBlock].level;
             bool exact = true;                                        // `cur` is the reference's value, not an assumption
             for (int b = R[r].b0; b < R[r].b1; b++) {
                 const int ns = (int) c->h_nsub[b];
@@ -400,6 +411,7 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
         if (nbad == 0) break;
         if (pass > nb * kMaxSubPerBlock + 4) return fail(ZLB_E_CUDA, "internal: level-feedback replay did not converge");
     }
+    if (mode == MODE_SPECULATE) { c->spec_reparsed = reparsed; return ZLB_OK; }
 
     // layout of the framed streams: per sub-block 1 + 12 + olen bytes, one stop byte per block; streams back to back
     unsigned long long off = 0, ntok = 0, nsub_total = 0;
@@ -441,7 +453,7 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
         c->stats.cyc_decide = c->h_v4c.cyc_decide;
         if (getenv("ZLB_V4_TRACE")) {
             fprintf(stderr, "v4 phases (cycles per window, summed over blocks / windows):");
-            for (int i = 0; i < 24; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
+            for (int i = 0; i < 32; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
             fprintf(stderr, "\n");
         }
     }
@@ -449,14 +461,14 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
 }
 
 // the stream API: ONE stream, n bytes = the next blocks of it
-static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after, int mode = MODE_ALL) {
+static int encode_device(zlb_encoder* e, const uint8_t* d_in, size_t n, uint8_t* d_out, size_t out_cap, size_t* out_len, int* level_after, int mode = MODE_ALL, const uint8_t* pre_tail = nullptr) {
     zlb_ctx* c = e->ctx;
     const int nb = (int) ((n + kBlockBytes - 1) / kBlockBytes);
     for (int b = 0; b < nb; b++) c->h_ilen[b] = (uint32_t) (b + 1 < nb ? (size_t) kBlockBytes : n - (size_t) b * kBlockBytes);
     EncRange R;
     R.b0 = 0; R.b1 = nb; R.level_in = e->cur_level; R.level_out = e->cur_level;
     R.st_in = e->d_state[e->cur]; R.st_out = e->d_state[e->cur ^ 1]; R.first_dirty = 0; R.out_off = R.out_len = 0;
-    const int rc = encode_ranges(c, e->level, d_in, nb, &R, 1, d_out, out_cap, out_len, mode);
+    const int rc = encode_ranges(c, e->level, d_in, nb, &R, 1, d_out, out_cap, out_len, mode, pre_tail);
     if (rc) return rc;
     *level_after = R.level_out;       // the caller commits (state ping-pong + level) once the call has succeeded
     return ZLB_OK;
@@ -632,18 +644,20 @@ int zlb_encode_complete(zlb_encoder* e, uint8_t* out, size_t out_cap, size_t* ou
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
+static constexpr size_t kTailBytes = 65536 + 16;
 struct zlb_comm {
     zlb_ctx* ctx = nullptr;
     ncclComm_t nccl = nullptr;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;          // exchange stream: the carry can arrive while the parse kernel runs on ctx->stream
     uint8_t* d_carry = nullptr;             // ZLB_STATE_BYTES (MTF tables + int32 level), padded
+    uint8_t* d_tail = nullptr;              // [2][kTailBytes]: the 64 KiB before this rank's range + u32 valid flag (received), the same for the next rank (sent)
     unsigned long long* d_sizes = nullptr;  // [world + 1]: [world] = this rank's size (all-gather input)
     unsigned long long* h_sizes = nullptr;  // pinned mirror, [world + 1]
     int32_t* h_level = nullptr;             // pinned
     uint8_t* d_all = nullptr;               // rank 0: the gathered stream
     size_t all_cap = 0;
-    cudaEvent_t ev[4] = {};
+    cudaEvent_t ev[6] = {};
     zlb_shard_stats stats = {};
 };
 #define NC(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
@@ -664,7 +678,7 @@ void zlb_comm_destroy(zlb_comm* m) {
     cudaSetDevice(m->ctx->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->nccl && nccl_api().CommDestroy) nccl_api().CommDestroy(m->nccl);
-    cudaFree(m->d_carry); cudaFree(m->d_sizes); cudaFree(m->d_all);
+    cudaFree(m->d_carry); cudaFree(m->d_sizes); cudaFree(m->d_all); cudaFree(m->d_tail);
     if (m->h_sizes) cudaFreeHost(m->h_sizes);
     if (m->h_level) cudaFreeHost(m->h_level);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
@@ -682,6 +696,7 @@ zlb_comm* zlb_comm_create(zlb_ctx* c, int rank, int world, const uint8_t* id) {
     ncclUniqueId u; memcpy(&u, id, sizeof u);
     bool ok = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&m->d_carry, ZLB_STATE_BYTES + 60) == cudaSuccess &&
+              cudaMalloc(&m->d_tail, 2 * kTailBytes) == cudaSuccess &&
               cudaMalloc(&m->d_sizes, ((size_t) world + 1) * 8) == cudaSuccess &&
               cudaHostAlloc(&m->h_sizes, ((size_t) world + 1) * 8, cudaHostAllocDefault) == cudaSuccess &&
               cudaHostAlloc(&m->h_level, 64, cudaHostAllocDefault) == cudaSuccess;
@@ -815,9 +830,45 @@ int zlb_encode_stream_sharded(zlb_encoder* e, zlb_comm* m, const uint8_t* in, si
             CU(cudaMemsetAsync(c->d_in + n, 0, 64, c->stream));
         }
         CU(cudaEventRecord(c->ev[EV_H2D], c->stream));
-        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SUBMIT);
+    }
+    // 1a. the 64 KiB in front of every range travel to the rank that owns it (the parse predicts the level of the range's first
+    // sub-block from them, like it does for every block behind the first of a call); an empty range forwards what it received
+    uint8_t* tail_in = m->d_tail, *tail_out = m->d_tail + kTailBytes;
+    if (m->world > 1) {
+        CU(cudaEventRecord(m->ev[4], c->stream));
+        CU(cudaStreamWaitEvent(m->stream, m->ev[4], 0));
+        if (m->rank > 0) NC(nc.Recv(tail_in, kTailBytes, ncclUint8, m->rank - 1, m->nccl, m->stream));
+        else CU(cudaMemsetAsync(tail_in, 0, kTailBytes, m->stream));
+        if (m->rank + 1 < m->world) {
+            if (n >= 65536) {
+                CU(cudaMemcpyAsync(tail_out, d_in + n - 65536, 65536, cudaMemcpyDeviceToDevice, m->stream));
+                CU(cudaMemsetAsync(tail_out + 65536, 1, 1, m->stream));
+            } else if (n == 0) {
+                CU(cudaMemcpyAsync(tail_out, tail_in, kTailBytes, cudaMemcpyDeviceToDevice, m->stream));
+            } else {
+                CU(cudaMemsetAsync(tail_out, 0, kTailBytes, m->stream));
+            }
+            NC(nc.Send(tail_out, kTailBytes, ncclUint8, m->rank + 1, m->nccl, m->stream));
+        }
+        CU(cudaEventRecord(m->ev[5], m->stream));
+        CU(cudaStreamWaitEvent(c->stream, m->ev[5], 0));
+    }
+    const uint8_t* pre_tail = (m->world > 1 && m->rank > 0) ? tail_in : nullptr;
+    if (n) {
+        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SUBMIT, pre_tail);
         if (rc) return rc;
     }
+    // 1b. ranks behind the first: finish the level feedback of the range BEFORE the carried state is there.  The levels depend
+    // on the Huffman sizes of the sub-blocks (libzling.cpp:261-266), those on the MTF ranks, those on the carried tables — but
+    // only through the first few thousand literals of the range, so ranks computed from this encoder's current tables give
+    // the same levels except on a knife's edge.  Mispredicted blocks are re-parsed now, concurrently on all ranks; the exact
+    // pass below (step 3) verifies everything against the real carried state and repairs what is left.
+    c->spec_reparsed = 0;
+    if (n && m->rank > 0) {
+        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_SPECULATE, pre_tail);
+        if (rc) return rc;
+    }
+    m->stats.spec_reparsed_blocks = c->spec_reparsed;
     // 2. the carried state of the previous range, GPU -> GPU, while the parse runs
     CU(cudaEventRecord(m->ev[0], m->stream));
     if (m->rank > 0) {
@@ -832,7 +883,7 @@ int zlb_encode_stream_sharded(zlb_encoder* e, zlb_comm* m, const uint8_t* in, si
     }
     // 3. MTF ranks + Huffman + framing of the range (re-parses its first block only if the carried level differs)
     if (n) {
-        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_COMPLETE);
+        const int rc = encode_device(e, d_in, n, c->d_out, c->out_cap, &produced, &level_after, MODE_COMPLETE, pre_tail);
         if (rc) return rc;
         CU(cudaEventRecord(c->ev[EV_END], c->stream));
         CU(cudaStreamSynchronize(c->stream));

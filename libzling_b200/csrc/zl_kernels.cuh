@@ -93,6 +93,7 @@ struct ParseArgs {
     uint32_t*       nsub;      // [nblocks]
     uint32_t*       ntok;      // [nblocks]
     uint32_t*       nlit;      // [nblocks]
+    const uint8_t*  pre_tail;  // null, or 65536 bytes that precede block 0 in its stream + a u32 'valid' flag (ranges of a sharded stream)
 };
 
 }  // namespace zl

@@ -973,14 +973,15 @@ struct V4Run {
 };
 // Level of sub-block j.  The reference derives it from the PREVIOUS sub-block's Huffman size (src/libzling.cpp:261-266:
 // olen / (consumed + 1) > 0.95 => level 0), which is not known during the parse (the literal ranks depend on MTF state
-// carried across blocks).  plan[j] is the host's word: a level it has verified, or kV4Auto = "predict": a sub-block
-// that is almost all single-byte symbols (consumed <= 1.125 x symbols) will not compress.  The host verifies every
-// level afterwards from the real sizes and re-parses from the first wrong one, so a wrong guess only costs time.
+// carried across blocks).  plan[j] is the host's word: a level it has verified, or kV4Auto = "predict": apply the reference's
+// rule with one byte per symbol as the size estimate (what incompressible data costs: its symbols are literals of ~8 bits;
+// measured on the mixed corpus: 1 wrong guess in 1716 sub-blocks).  The host verifies every level afterwards from the
+// real sizes and re-parses from the first wrong one, so a wrong guess only costs time.
 ZL_HD int v4_next_level(const V4Ctx& c, int j, int consumed, int op) {
     const uint32_t p = c.plan[j < kMaxSubPerBlock ? j : kMaxSubPerBlock - 1];
     if (p != kV4Auto) return (int) p;
     if (j == 0) return c.base_level;
-    return consumed <= op + (op >> 3) ? 0 : c.base_level;
+    return (unsigned long long) op * 20ull > (unsigned long long) (consumed + 1) * 19ull ? 0 : c.base_level;
 }
 ZL_HD void v4_close_subblock(const V4Ctx& c, const V4Run& r, int ip, int op, int nt) {
     if (r.j < kMaxSubPerBlock) {
@@ -1032,7 +1033,7 @@ ZL_HD void v4_resolve_tail(const V4Ctx& c, V4Run& r, int* nt_io, int* nl_io) {
 namespace zl {
 namespace cg = cooperative_groups;
 
-struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[24]; };
+struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[32]; };
 
 __device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
 // warp 0: per-warp totals arr[0..31] -> exclusive prefix in place, grand total in arr[32] (callers synchronise around it)
@@ -1063,13 +1064,28 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ V4Win s_win;
     __shared__ int s_nt, s_nl, s_exit, s_lastrel, s_rpos_rel, s_rpos_nt, s_op_at_rpos;
     __shared__ int s_wtok[33], s_wlit[33], s_wsym[33], s_wsya[33];
-    __shared__ uint32_t s_dmax[4];
+    __shared__ unsigned s_wmax[4];                                               // profiling build: per-round maxima over the warps
     __shared__ int s_take[4];                                                    // next entry to take from the stage queues
     __shared__ int s_nq[4];                                                      // queue lengths of the decide stages
-    __shared__ unsigned long long s_ph[24];                                      // phase timers (thread 0's clock between barriers)
+    __shared__ unsigned long long s_ph[32];                                      // phase timers (thread 0's clock between barriers)
     long long tprev = 0;
 #define V4_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); s_ph[i] += (unsigned long long) (now_ - tprev); tprev = now_; } } while (0)
-    if (tid < 24) s_ph[tid] = 0;
+    if (tid < 32) s_ph[tid] = 0;
+    if (tid < 4) s_wmax[tid] = 0;
+#if defined(ZL_V4_PROFILE)
+    long long wt_ = 0;
+#define V4_WT0() do { wt_ = clock64(); } while (0)
+#define V4_WTICK(i) do { if (tid == 992) { const long long n_ = clock64(); s_ph[i] += (unsigned long long) (n_ - wt_); wt_ = n_; } } while (0)
+#define V4_WMAX(i, v) do { if (lane == 0) atomicMax(&s_wmax[i], (unsigned) (v)); } while (0)
+#define V4_WADD(i, v) do { if (lane == 0) atomicAdd(&s_wmax[i], (unsigned) (v)); } while (0)
+#define V4_PADD(i, v) do { if (lane == 0) atomicAdd(&s_ph[i], (unsigned long long) (v)); } while (0)
+#else
+#define V4_WT0() do { } while (0)
+#define V4_WTICK(i) do { } while (0)
+#define V4_WMAX(i, v) do { } while (0)
+#define V4_WADD(i, v) do { } while (0)
+#define V4_PADD(i, v) do { } while (0)
+#endif
     static_assert(kV4T == 1024, "the kernel assumes 32 warps (prefix helpers, wcnt rows, link groups)");
     const V4Layout L = v4_layout(dmax, lmax);
     V4Ctx c;
@@ -1149,9 +1165,10 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     // the previous block's last 64 KiB: data that Huffman cannot shrink below 0.95 of its size (the reference's rule) has
     // a near-uniform byte histogram.  The host verifies the level afterwards and re-parses on a wrong guess.
     int level0_pred = base_level;
-    if (b > 0 && a.plan[(size_t) b * kMaxSubPerBlock] == kV4Auto && base_level != 0) {
+    const bool has_pre = b > 0 || (a.pre_tail && a.pre_tail[65536]);     // block 0 of a sharded range: the bytes in front of it came from the rank before
+    if (has_pre && a.plan[(size_t) b * kMaxSubPerBlock] == kV4Auto && base_level != 0) {
         __syncthreads();
-        const uint8_t* tail = c.in - 65536;                              // the previous block's tail (blocks are contiguous, full except the last)
+        const uint8_t* tail = b > 0 ? c.in - 65536 : a.pre_tail;         // the previous block's tail (blocks are contiguous, full except the last)
         for (int i = tid * 16; i < 65536; i += kV4T * 16) {
             const uint4 v = z4_ld_in128(reinterpret_cast<const uint4*>(tail + i));
             const uint32_t wv[4] = { v.x, v.y, v.z, v.w };
@@ -1189,6 +1206,9 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     const int nwin = lim > 2 ? (lim + kV4W - 1) / kV4W : 0;              // windows that contain probe positions
     int staged_hi = -16;
     const int segbase = warp * 32, segend = segbase + 32;
+    uint32_t* const tabA = c.mcnt;                                       // per-round tables, set 0: mcnt, pushw, pf, plit as laid out
+    uint32_t* const tabB = reinterpret_cast<uint32_t*>(scratch + 32768); // set 1 lives in the scratch area (free during the rounds)
+    uint32_t* const pushwA = c.pushw; uint32_t* const pfA = c.pf; uint8_t* const plitA = c.plit;
 
     for (int k = 0; k < nwin; k++) {
         const int lo = k * kV4W;
@@ -1267,26 +1287,39 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         const long long t1 = clock64();
         cyc_spec += t1 - t0;
         // ================================================= ROUNDS ===============================================
+        // Three barriers per round: (1) orbit tables ready — it also carries the vote "did the previous round change a decision";
+        // (2) marks + per-round tables + stage queues ready; (3) decisions of the round written.  The per-round tables
+        // (mcnt, pushw, pf, plit) exist twice, so that the set of the next round is cleared while this round's is still read
+        // (and FINALIZE finds the set of the last round untouched).
         const int entry_rel = s_win.entry - lo;
         const bool may_roll = s_run.op + 2 * kV4N + 1 >= kSubSymbols;
         bool marked = false;
+        uint32_t mydec = c.dec[tid];
+        int par = 0, ch = 1;
         while (true) {
-            n_rounds++;
             const long long r0 = clock64();
             // ---- orbit of the entry under next = x + step(decision).  Inside a 32-position segment: pointer doubling with
             // shuffles; across segments: every warp chases the segment exits from the window's entry up to its own segment
-            const uint32_t mydec = c.dec[tid];
             int cj[6];
             { int t = tid < Wn ? tid + (int) v4_dec_step(mydec) : Wn; cj[0] = t < Wn ? t : Wn; }
             #pragma unroll
             for (int l = 0; l < 5; l++) { const int nx = __shfl_sync(0xffffffffu, cj[l], cj[l] & 31); cj[l + 1] = cj[l] < segend ? nx : cj[l]; }
             E[tid] = (uint16_t) cj[5];
-            c.plit[tid] = 0;
-            if (tid < 256) { c.mcnt[tid] = 0; c.pushw[tid] = 0; }
-            if (tid >= 256 && tid < 256 + kV4PfWords) c.pf[tid - 256] = 0;
+            uint32_t* const n_mcnt = par ? tabB : tabA;
+            uint32_t* const n_pushw = par ? tabB + 256 : pushwA;
+            uint32_t* const n_pf = par ? tabB + 512 : pfA;
+            uint8_t* const n_plit = par ? reinterpret_cast<uint8_t*>(tabB + 512 + kV4PfWords) : plitA;
+            n_plit[tid] = 0;
+            if (tid < 256) { n_mcnt[tid] = 0; n_pushw[tid] = 0; }
+            if (tid >= 256 && tid < 256 + kV4PfWords) n_pf[tid - 256] = 0;
             if (tid == 0) s_rpos_rel = 0x7fffffff;
             if (tid < 3) { s_nq[tid] = 0; s_take[tid] = 0; }
-            __syncthreads();
+            const int changed = __syncthreads_or(ch);                    // barrier 1
+            if (!changed) break;
+            n_rounds++;
+            c.mcnt = n_mcnt; c.pushw = n_pushw; c.pf = n_pf; c.plit = n_plit;
+            cc.mcnt = n_mcnt; cc.pushw = n_pushw; cc.pf = n_pf; cc.plit = n_plit;
+            V4_WT0();
             int cur = entry_rel;
             while ((cur >> 5) < warp && cur < Wn) cur = E[cur];
             uint32_t M = ((cur >> 5) == warp && cur < Wn) ? 1u << (cur & 31) : 0u;
@@ -1296,9 +1329,11 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 const uint32_t contrib = (((M >> lane) & 1u) && tg < segend && tg < Wn) ? 1u << (tg & 31) : 0u;
                 M |= __reduce_or_sync(0xffffffffu, contrib);
             }
+            V4_WTICK(9);
             marked = (M >> lane) & 1u;
             c.mark[tid] = (uint8_t) marked;
             if (lane == 0) c.mbits[warp] = M;
+            V4_WTICK(10);
             {   // mcnt[ctx] = marked positions per context (bounds the inserts a record can have missed)
                 const uint32_t cv = marked ? v4_ctx_of(c.key[tid]) : 256u + (uint32_t) lane;
                 const uint32_t grp = __match_any_sync(0xffffffffu, cv);
@@ -1314,7 +1349,37 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
                 else { s_exit = lo + t; s_lastrel = tid; }
             }
+            // ---- stage A: every MARKED position classifies itself (unmarked ones keep their frozen decision until the orbit
+            // reaches them) into the queues of the stages below: 0 hazard check, 1 full probe, 2 word test
+            auto classify = [&](const V4Win& w) {
+                uint32_t nd = mydec;
+                const int level_here = (w.rpos >= 0 && lo + tid >= w.rpos) ? w.level2 : w.level;
+                int which = -1;
+                if (marked && tid >= entry_rel && tid < Wn) {
+                    const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
+                    if (level_here != w.level) which = 1;
+                    else if (fxw >> 16) which = 0;
+                    else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
+                    else which = 2;
+                }
+                #pragma unroll
+                for (int qi = 0; qi < 3; qi++) {                         // one shared-memory atomic per warp and queue
+                    const uint32_t bal = __ballot_sync(0xffffffffu, which == qi);
+                    if (bal) {
+                        int base = 0;
+                        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_nq[qi], __popc(bal));
+                        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+                        if (which == qi) (qi == 0 ? qhaz : qi == 1 ? qgen : qmru)[base + __popc(bal & v4_lt_mask(lane))] = (uint16_t) tid;
+                    }
+                }
+                c.ndec[tid] = nd;
+            };
             const long long r1 = clock64();
+            V4_WTICK(11);
+            if (!may_roll) classify(s_win);
+            V4_WTICK(15);
+            __syncthreads();                                             // barrier 2
+            V4_TICK(13);
             // ---- sub-block roll-over (rare): symbols before each marked position
             if (may_roll) {
                 const uint32_t mysym = marked ? v4_dec_syms(mydec) : 0u;
@@ -1339,45 +1404,17 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                     }
                     s_win = w;
                 }
+                __syncthreads();
+                classify(s_win);
+                __syncthreads();
             }
-            __syncthreads();
             const long long r2 = clock64();
-            // ---- every MARKED position re-derives its decision (unmarked ones keep their frozen decision until the orbit reaches
-            // them).  The work is staged through queues so that each piece of code runs on a dense set of positions, one
-            // position per warp first (the stages are bound by instruction issue: a warp pays for a path as soon as one of
-            // its lanes takes it): A classify -> B hazard checks -> C full probes on the pending view -> D word-MRU tests
+            // ---- stages B + C + D without barriers between them: the warps take hazard-check entries one at a time (cc.coop = 1:
+            // the 32 lanes evaluate the entry together), run the full probe right away when the hazard holds and the word test when
+            // the probe finds no match; a warp that finds no entry left turns to the word tests stage A queued (one per lane)
             const V4Win w = s_win;
-            uint32_t nd = mydec;
-            const int level_here = (w.rpos >= 0 && lo + tid >= w.rpos) ? w.level2 : w.level;
-            {
-                int which = -1;                                          // queue this position goes to: 0 hazard check, 1 full probe, 2 word test
-                if (marked && tid >= entry_rel && tid < Wn) {
-                    const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
-                    if (level_here != w.level) which = 1;
-                    else if (fxw >> 16) which = 0;
-                    else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
-                    else which = 2;
-                }
-                #pragma unroll
-                for (int qi = 0; qi < 3; qi++) {                         // one shared-memory atomic per warp and queue
-                    const uint32_t bal = __ballot_sync(0xffffffffu, which == qi);
-                    if (bal) {
-                        int base = 0;
-                        if (lane == __ffs(bal) - 1) base = atomicAdd(&s_nq[qi], __popc(bal));
-                        base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-                        if (which == qi) (qi == 0 ? qhaz : qi == 1 ? qgen : qmru)[base + __popc(bal & v4_lt_mask(lane))] = (uint16_t) tid;
-                    }
-                }
-            }
-            c.ndec[tid] = nd;
-            tprev = r2;
-            __syncthreads();
-            V4_TICK(13);
-            // stages B + C + D without barriers between them: the warps take hazard-check entries one at a time (cc.coop = 1: the 32
-            // lanes evaluate the entry together) and run the full probe right away when the hazard holds; a warp that finds no
-            // entry left turns to the word tests stage A queued (one per lane).  Word tests queued late (positions whose probe
-            // found no match) wait for the barrier.
-            const int n_haz = s_nq[0], n_gen = s_nq[1], n_mru = s_nq[2];     // what stage A queued (stable: read behind its barrier)
+            const int n_haz = s_nq[0], n_gen = s_nq[1], n_mru = s_nq[2];     // stable: read behind barrier 2
+            int n_items = 0; (void) n_items;
             while (true) {
                 int i = 0;
                 if (lane == 0) i = atomicAdd(&s_take[0], 1);
@@ -1386,13 +1423,29 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 const int rel = i < n_haz ? qhaz[i] : qgen[i - n_haz];
                 const uint32_t fd = c.fdec[rel];
                 uint32_t len = fd & 511u, rf = (fd >> 18) & (kRing - 1);
+                n_items++;
+#if defined(ZL_V4_PROFILE)
+                const long long i0_ = clock64();
+                const bool hz_ = i >= n_haz || v4_hazard(cc, rel, fd, c.fx[rel], depth_lazy2(w.level));
+                const long long i1_ = clock64();
+                V4_PADD(24, i1_ - i0_); V4_PADD(25, 1);
+                if (hz_) {
+                    len = (uint32_t) v4_probe_general(cc, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
+                    V4_WADD(3, 1);
+                    V4_PADD(26, clock64() - i1_); V4_PADD(27, 1);
+                }
+                const long long i2_ = clock64();
+                const uint32_t nd = len ? v4_dec_match(len, rf) : v4_decide_word(cc, w, rel);
+                if (!len) { V4_PADD(28, clock64() - i2_); V4_PADD(29, 1); }
+                V4_WMAX(2, clock64() - i0_);                              // slowest single entry of the round
+#else
                 if (i >= n_haz || v4_hazard(cc, rel, fd, c.fx[rel], depth_lazy2(w.level)))
                     len = (uint32_t) v4_probe_general(cc, lo, rel, (w.rpos >= 0 && lo + rel >= w.rpos) ? w.level2 : w.level, &rf);
-                if (lane == 0) {
-                    if (len) c.ndec[rel] = v4_dec_match(len, rf);
-                    else qmru[atomicAdd(&s_nq[2], 1)] = (uint16_t) rel;
-                }
+                const uint32_t nd = len ? v4_dec_match(len, rf) : v4_decide_word(cc, w, rel);
+#endif
+                if (lane == 0) c.ndec[rel] = nd;
             }
+            V4_WMAX(0, clock64() - r2);
             while (true) {
                 int i0 = 0;
                 if (lane == 0) i0 = atomicAdd(&s_take[1], 32);
@@ -1400,21 +1453,21 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (i0 >= n_mru) break;
                 if (i0 + lane < n_mru) { const int rel = qmru[i0 + lane]; c.ndec[rel] = v4_decide_word(c, w, rel); }
             }
-            __syncthreads();
+            V4_WMAX(1, clock64() - r2);
+            __syncthreads();                                             // barrier 3
             V4_TICK(14);
-            if (tid == 0) { s_ph[20] += (unsigned long long) n_haz; s_ph[21] += (unsigned long long) n_gen; s_ph[22] += (unsigned long long) s_nq[2]; }
-            {   // the late word tests: one per thread, spread over the warps
-                const int qslot = n_mru + lane * 32 + warp;
-                if (qslot < s_nq[2]) { const int rel = qmru[qslot]; c.ndec[rel] = v4_decide_word(c, w, rel); }
+            if (tid == 0) {
+                s_ph[20] += (unsigned long long) n_haz; s_ph[21] += (unsigned long long) n_gen + s_wmax[3]; s_ph[22] += (unsigned long long) n_mru;
+                s_ph[16] += s_wmax[0]; s_ph[17] += s_wmax[1]; s_ph[18] += s_wmax[2];
+                s_wmax[0] = s_wmax[1] = s_wmax[2] = s_wmax[3] = 0;
             }
-            __syncthreads();
-            V4_TICK(19);
-            nd = c.ndec[tid];
-            const int changed = __syncthreads_or(marked && ((nd ^ mydec) & kV4DecCmp) != 0);
+            const uint32_t nd = c.ndec[tid];
+            ch = marked && ((nd ^ mydec) & kV4DecCmp) != 0;
             c.dec[tid] = nd;
+            mydec = nd;
+            par ^= 1;
             const long long r3 = clock64();
             cyc_orbit += r1 - r0; cyc_rank += r2 - r1; cyc_decide += r3 - r2;
-            if (!changed) break;
         }
         const long long t2 = clock64();
         tprev = t2;
@@ -1492,7 +1545,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             atomicAdd(&counters->cyc_rank, (unsigned long long) cyc_rank);
             atomicAdd(&counters->cyc_decide, (unsigned long long) cyc_decide);
             atomicAdd(&counters->cyc_total, (unsigned long long) (clock64() - t_begin));
-            for (int i = 0; i < 24; i++) atomicAdd(&counters->ph[i], s_ph[i]);
+            for (int i = 0; i < 32; i++) atomicAdd(&counters->ph[i], s_ph[i]);
         }
     }
 }
