@@ -67,7 +67,7 @@ struct zlb_ctx {
     const void* pending = nullptr;  // encoder with a submitted, not yet completed range: it owns the context's buffers
     V4Counters* d_v4c = nullptr;
     V4Counters  h_v4c = {};
-    int parse_cluster = 0;          // CTAs per block of the parse kernel; 0 = choose by the number of blocks (ZLB_PARSE_CLUSTER=1|2|4|8 pins it)
+    int parse_cluster = 0;          // CTAs per block of the parse kernel; 0 = choose by the number of blocks (ZLB_PARSE_CLUSTER=1|2|4|8|16 pins it)
     uint32_t *d_lbuf = nullptr, *d_lhist = nullptr, *d_ctxoff = nullptr;
     MtfRange *d_mrng = nullptr, *h_mrng = nullptr;   // per-stream block ranges of the MTF pass (max_blocks entries)
     uint8_t* d_bstate = nullptr;                     // batch API: initial MTF tables + one scratch table per stream, allocated on first use
@@ -182,7 +182,13 @@ static int ctx_alloc(zlb_ctx* c) {
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(6, 2).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(8, 3).total));
     CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, v4_layout(16, 4).total));
-    { const char* pv = getenv("ZLB_PARSE_CLUSTER"); if (pv && (*pv == '1' || *pv == '2' || *pv == '4' || *pv == '8') && !pv[1]) c->parse_cluster = *pv - '0'; }
+    // clusters of 16 CTAs are beyond the portable size (8): opt in per kernel
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<2, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<4, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<6, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<8, 3>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    CU(cudaFuncSetAttribute(zl_rolz_parse_v4_kernel<16, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    { const char* pv = getenv("ZLB_PARSE_CLUSTER"); if (pv) { const int v = atoi(pv); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) c->parse_cluster = v; } }
     CU(cudaFuncSetAttribute(zl_huff_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     CU(cudaFuncSetAttribute(zl_rolz_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     return ZLB_OK;
@@ -453,8 +459,20 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
         c->stats.cyc_decide = c->h_v4c.cyc_decide;
         if (getenv("ZLB_V4_TRACE")) {
             fprintf(stderr, "v4 phases (cycles per window, summed over blocks / windows):");
-            for (int i = 0; i < 32; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
+            for (int i = 0; i < 40; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
             fprintf(stderr, "\n");
+#if defined(ZL_V4_PROFILE)
+            {
+                unsigned long long gp[16];
+                if (cudaMemcpyFromSymbol(gp, zl::g_v4prof, sizeof gp) == cudaSuccess) {
+                    fprintf(stderr, "v4 probe profile (totals):");
+                    for (int i = 0; i < 16; i++) fprintf(stderr, " g%d=%llu", i, gp[i]);
+                    fprintf(stderr, "\n");
+                    memset(gp, 0, sizeof gp);
+                    cudaMemcpyToSymbol(zl::g_v4prof, gp, sizeof gp);
+                }
+            }
+#endif
         }
     }
     return ZLB_OK;

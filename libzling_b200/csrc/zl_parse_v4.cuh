@@ -716,6 +716,16 @@ ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, int L2)
     return false;
 }
 
+#if defined(ZL_V4_PROFILE) && defined(__CUDACC__)
+__device__ unsigned long long g_v4prof[16];
+#endif
+#if defined(ZL_V4_PROFILE) && defined(__CUDA_ARCH__)
+#define V4_GP_T() clock64()
+#define V4_GP(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_v4prof[i], (unsigned long long) (v)); } while (0)
+#else
+#define V4_GP_T() 0ll
+#define V4_GP(i, v) do { } while (0)
+#endif
 // The full MatchAndUpdate (lz.cpp:211-289) at rel on the pending view: in-window candidates (newest first), then the
 // frozen record.  Returns the match length (0 = none) and the reference to the best candidate (a ring slot, or
 // kV4RefWin | rel of a pending position).
@@ -728,12 +738,15 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
     int best = kMinLen - 1, visited = 0, first_pending = -1;
     uint32_t ref = 0;
     bool done = false;
+    const long long g0_ = V4_GP_T();
+    int hops_ = 0; (void) hops_;
     {
         int y = rel;
         while (true) {
             const uint32_t dl = c.link[y];
             if (!dl) break;
             y -= (int) dl;
+            hops_++;
             if (!c.mark[y]) continue;
             if (first_pending < 0) first_pending = y;
             if (visited < D && !done) {
@@ -745,6 +758,8 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
             } else break;
         }
     }
+    const long long g1_ = V4_GP_T();
+    V4_GP(0, g1_ - g0_); V4_GP(1, hops_); V4_GP(2, visited);
     const uint32_t hdr = c.hdr[rel];
     int nvis = (int) (hdr & 31u);
     bool stale0 = false;
@@ -774,7 +789,10 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
             }
         }
     }
+    const long long g2_ = V4_GP_T();
+    V4_GP(3, g2_ - g1_); V4_GP(4, stale0 ? 1 : 0);
     if (best < kMinLen) return 0;
+    V4_GP(5, 1);
     if (best < kLazyBelow) {                                             // lz.cpp:270-281
         const uint32_t at = (uint32_t) best - 3u;
         for (int which = 1; which <= 2; which++) {
@@ -811,6 +829,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
                 if (v4_lazy_node_hit(c, relz, i, at, mine)) return 0;
         }
     }
+    V4_GP(6, V4_GP_T() - g2_);
     *ref_out = ref;
     return best;
 }
@@ -1033,7 +1052,7 @@ ZL_HD void v4_resolve_tail(const V4Ctx& c, V4Run& r, int* nt_io, int* nl_io) {
 namespace zl {
 namespace cg = cooperative_groups;
 
-struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[32]; };
+struct V4Counters { unsigned long long tokens, windows, rounds, decides_general, cyc_spec, cyc_rounds, cyc_final, cyc_total, cyc_orbit, cyc_rank, cyc_decide, ph[40]; };
 
 __device__ __forceinline__ uint32_t v4_lt_mask(int lane) { return (1u << lane) - 1u; }
 // warp 0: per-warp totals arr[0..31] -> exclusive prefix in place, grand total in arr[32] (callers synchronise around it)
@@ -1044,6 +1063,40 @@ __device__ __forceinline__ void v4_warp0_prefix(int* arr, int lane) {
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     arr[lane] = incl - v;
     if (lane == 31) arr[32] = incl;
+}
+
+// ---- SPEC B + C for a whole CTA: link[t] = distance to the nearest earlier position of the window with the same key.  First the
+// nearest earlier position in the same BUCKET (blink): groups of 4 warps own a bucket table (gtab, zeroed by the caller); inside a
+// group the warps take turns in position order, then positions without a predecessor in their own group look at the final tables
+// of the groups before theirs.  Then every position follows its bucket chain to the first equal key.  key[] must be complete.
+__device__ __forceinline__ void v4_build_links_cta(const V4Ctx& c, uint16_t* gtab, int tid, int lane, int warp) {
+    const int g = warp >> 2, turn = warp & 3;
+    uint16_t* tg = gtab + g * kV4Buckets;
+    const uint32_t kx = c.key[tid];
+    const bool valid = !(kx & kV4KeyInvalid);
+    const uint32_t bk = valid ? v4_bucket_of(kx) : 0xffff0000u + (uint32_t) lane;
+    uint32_t dist = 0;
+    const uint32_t grp = __match_any_sync(0xffffffffu, bk);              // same-bucket lanes of this warp (all warps at once; only the
+    const uint32_t lower = grp & v4_lt_mask(lane);                       // table look-ups below have to go in position order)
+    if (valid && lower) dist = (uint32_t) lane - (31u - (uint32_t) __clz(lower));
+    for (int i = 0; i < 4; i++) {
+        if (turn == i) {
+            if (valid && !lower) { const uint32_t prev = tg[bk]; if (prev) dist = (uint32_t) tid - (prev - 1u); }
+            __syncwarp();
+            if (valid && (grp >> lane) == 1u) tg[bk] = (uint16_t) (tid + 1);
+        }
+        asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory");
+    }
+    __syncthreads();
+    if (valid && dist == 0) {
+        for (int g2 = g - 1; g2 >= 0; g2--) {
+            const uint32_t prev = gtab[g2 * kV4Buckets + bk];
+            if (prev) { dist = (uint32_t) tid - (prev - 1u); break; }
+        }
+    }
+    c.blink[tid] = (uint16_t) dist;
+    __syncthreads();
+    v4_link_position(c, tid);
 }
 
 // ---- the kernel: grid = blocks of the batch, kV4T threads, thread t owns position lo + t of the current window -----------
@@ -1067,10 +1120,10 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
     __shared__ unsigned s_wmax[4];                                               // profiling build: per-round maxima over the warps
     __shared__ int s_take[4];                                                    // next entry to take from the stage queues
     __shared__ int s_nq[4];                                                      // queue lengths of the decide stages
-    __shared__ unsigned long long s_ph[32];                                      // phase timers (thread 0's clock between barriers)
+    __shared__ unsigned long long s_ph[40];                                      // phase timers (thread 0's clock between barriers)
     long long tprev = 0;
 #define V4_TICK(i) do { if (tid == 0) { const long long now_ = clock64(); s_ph[i] += (unsigned long long) (now_ - tprev); tprev = now_; } } while (0)
-    if (tid < 32) s_ph[tid] = 0;
+    if (tid < 40) s_ph[tid] = 0;
     if (tid < 4) s_wmax[tid] = 0;
 #if defined(ZL_V4_PROFILE)
     long long wt_ = 0;
@@ -1104,10 +1157,14 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         uint32_t* l_nodeq = cluster.map_shared_rank(c.nodeq, 0); uint32_t* l_fx = cluster.map_shared_rank(c.fx, 0);
         uint32_t* l_fdec = cluster.map_shared_rank(c.fdec, 0);
         const V4Run* leader_run = cluster.map_shared_rank(&s_run, 0);
-        const int H = CL - 1, chunk = (kV4N + H - 1) / H;
+        const bool link_helper = CL >= 4;                                // the last helper builds the window's links instead of walking chains
+        const bool i_link = link_helper && crank == CL - 1;
+        uint16_t* l_link = cluster.map_shared_rank(c.link, 0);
+        const int H = link_helper ? CL - 2 : CL - 1, chunk = (kV4N + H - 1) / H;
         const int r0 = (crank - 1) * chunk, r1 = r0 + chunk < kV4N ? r0 + chunk : kV4N;
         const int r2 = r1 + 2 < kV4N ? r1 + 2 : kV4N;                    // two more records: the lazy tests of the last positions look at them
-        const int T = kV4T / (r2 - r0) < 1 ? 1 : (kV4T / (r2 - r0) > DMAX ? DMAX : kV4T / (r2 - r0));   // threads per position in the compare step
+        const int span = r2 - r0 > 0 ? r2 - r0 : 1;
+        const int T = kV4T / span < 1 ? 1 : (kV4T / span > DMAX ? DMAX : kV4T / span);   // threads per position in the compare step
         uint32_t* qall = reinterpret_cast<uint32_t*>(smem_raw + L.scratch);   // [kV4N * DMAX] candidate positions (the helpers do not use the scratch area otherwise)
         const int hlim = ilen - kGuard;
         const int hnwin = hlim > 2 ? (hlim + kV4W - 1) / kV4W : 0;
@@ -1119,16 +1176,36 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             for (int src = hstaged + tid * 16; src < hi; src += kV4T * 16) v4_stage16(c, src);
             hstaged = hi;
             __syncthreads();
+#if defined(ZL_V4_PROFILE)
+            long long ht_ = clock64();
+#define V4_HTICK(i) do { if (tid == 0 && (crank == 1 || i_link)) { const long long n_ = clock64(); s_ph[(i_link ? 36 : 32) + (i)] += (unsigned long long) (n_ - ht_); ht_ = n_; } } while (0)
+#else
+#define V4_HTICK(i) do { } while (0)
+#endif
             cluster.sync();                                              // B1: the leader has finished the previous window (G, counters, run state)
+            V4_HTICK(0);
             if (tid == 0) { s_hip = leader_run->ip; s_hlevel = leader_run->level; }
             __syncthreads();
             if (s_hip >= wend) continue;                                 // the leader skips this window too
+            if (i_link) {
+                uint16_t* gtab = reinterpret_cast<uint16_t*>(smem_raw + L.scratch);
+                c.key[tid] = v4_key_of(c, lo + tid);
+                { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4T) z[i] = make_uint4(0, 0, 0, 0); }
+                __syncthreads();
+                v4_build_links_cta(c, gtab, tid, lane, warp);
+                l_link[tid] = c.link[tid];
+                V4_HTICK(1);
+                cluster.sync();                                          // B2
+                V4_HTICK(2);
+                continue;
+            }
             const int rel = r0 + tid;
             if (rel < r2) {
                 c.key[rel] = v4_key_of(c, lo + rel);
                 v4_spec_walk(hc, lo, rel, qall);
             }
             __syncthreads();
+            V4_HTICK(1);
             {   // compares: T threads per position, each takes every T-th recorded node
                 const int prel = r0 + tid / T, sub = tid % T;
                 if (prel < r2) {
@@ -1145,15 +1222,22 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 for (int i = 0; i < nv; i++) l_node[rel * DMAX + i] = c.node[rel * DMAX + i];
                 for (int i = 0; i < nv && i < LMAX; i++) l_nodeq[rel * LMAX + i] = c.nodeq[rel * LMAX + i];
             }
+            V4_HTICK(2);
             cluster.sync();                                              // B2: records and frozen decisions are in the leader's shared memory
+            V4_HTICK(3);
         }
+#if defined(ZL_V4_PROFILE)
+        if (tid == 0 && counters && (crank == 1 || i_link)) for (int i = 32; i < 40; i++) atomicAdd(&counters->ph[i], s_ph[i]);
+#endif
         return;
     }
+    const bool link_helper = CL >= 4;                                    // the cluster's last CTA builds the links of every window
     V4Ctx cc = c;                                                        // the same state, evaluated by a whole warp per position
     cc.coop = 1;
     uint8_t* scratch = smem_raw + L.scratch;
     uint16_t* gtab = reinterpret_cast<uint16_t*>(scratch);                         // SPEC: [kV4Groups][kV4Buckets] last position + 1 per bucket
     uint16_t* E = reinterpret_cast<uint16_t*>(scratch);                            // ROUNDS: first position past its own 32-position segment on the orbit of each position
+    uint16_t* E4 = reinterpret_cast<uint16_t*>(scratch + 2048);                     // ROUNDS: the same for the 128-position group of each position
     uint16_t* qhaz = reinterpret_cast<uint16_t*>(scratch + 24576);                  // ROUNDS: positions waiting for the hazard check,
     uint16_t* qgen = qhaz + kV4T;                                                   //         for the full probe on the pending view,
     uint16_t* qmru = qgen + kV4T;                                                   //         for the word-MRU test
@@ -1226,7 +1310,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         c.key[tid] = v4_key_of(c, lo + tid);
         for (int i = tid; i < 256 * kV4Words; i += kV4T) c.occ[i] = 0;
         if (tid < 256) { c.pcnt[tid] = 0; c.occw[tid] = 0; }
-        { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4T) z[i] = make_uint4(0, 0, 0, 0); }
+        if (!link_helper) { uint4* z = reinterpret_cast<uint4*>(gtab); for (int i = tid; i < kV4ScratchSpec / 16; i += kV4T) z[i] = make_uint4(0, 0, 0, 0); }
         __syncthreads();
         V4_TICK(0);
         {   // occ: bit i of occ[v] <=> in[lo + i - 3] == v; thread t owns bit t (word = warp), threads 0..1 also bits N, N+1
@@ -1238,40 +1322,11 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
         }
         if (CL == 1) v4_spec_position(c, lo, tid);                       // chain records against G (with a cluster: done by the helper CTAs)
         V4_TICK(1);
-        {   // link builder: nearest earlier position of the window in the same bucket.  Groups of 4 warps own a bucket table;
-            // inside a group the warps take turns in position order, then positions without a predecessor in their own
-            // group look at the final tables of the groups before theirs.
-            const int g = warp >> 2, turn = warp & 3;
-            uint16_t* tg = gtab + g * kV4Buckets;
-            const uint32_t kx = c.key[tid];
-            const bool valid = !(kx & kV4KeyInvalid);
-            const uint32_t bk = valid ? v4_bucket_of(kx) : 0xffff0000u + (uint32_t) lane;
-            uint32_t dist = 0;
-            const uint32_t grp = __match_any_sync(0xffffffffu, bk);      // same-bucket lanes of this warp (all warps at once; only the
-            const uint32_t lower = grp & v4_lt_mask(lane);               // table look-ups below have to go in position order)
-            if (valid && lower) dist = (uint32_t) lane - (31u - (uint32_t) __clz(lower));
-            for (int i = 0; i < 4; i++) {
-                if (turn == i) {
-                    if (valid && !lower) { const uint32_t prev = tg[bk]; if (prev) dist = (uint32_t) tid - (prev - 1u); }
-                    __syncwarp();
-                    if (valid && (grp >> lane) == 1u) tg[bk] = (uint16_t) (tid + 1);
-                }
-                asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory");
-            }
+        if (!link_helper) {
+            v4_build_links_cta(c, gtab, tid, lane, warp);                // (with a cluster of >= 4 CTAs: done by the last helper CTA)
             __syncthreads();
-            V4_TICK(2);
-            if (valid && dist == 0) {
-                for (int g2 = g - 1; g2 >= 0; g2--) {
-                    const uint32_t prev = gtab[g2 * kV4Buckets + bk];
-                    if (prev) { dist = (uint32_t) tid - (prev - 1u); break; }
-                }
-            }
-            c.blink[tid] = (uint16_t) dist;
         }
-        __syncthreads();
         V4_TICK(3);
-        v4_link_position(c, tid);
-        __syncthreads();
         if (CL > 1) cluster.sync();                                      // B2: the helpers' records have arrived
         V4_TICK(4);
         const int wlevel = s_run.level;
@@ -1305,6 +1360,13 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             #pragma unroll
             for (int l = 0; l < 5; l++) { const int nx = __shfl_sync(0xffffffffu, cj[l], cj[l] & 31); cj[l + 1] = cj[l] < segend ? nx : cj[l]; }
             E[tid] = (uint16_t) cj[5];
+            {   // second level: first position past the own 128-position group (the four warps of the group synchronise among themselves)
+                asm volatile("bar.sync %0, 128;" :: "r"(1 + (warp >> 2)) : "memory");
+                const int gend = ((warp >> 2) + 1) * 128;
+                int e = cj[5];
+                while (e < gend && e < Wn) e = E[e];
+                E4[tid] = (uint16_t) e;
+            }
             uint32_t* const n_mcnt = par ? tabB : tabA;
             uint32_t* const n_pushw = par ? tabB + 256 : pushwA;
             uint32_t* const n_pf = par ? tabB + 512 : pfA;
@@ -1321,6 +1383,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             cc.mcnt = n_mcnt; cc.pushw = n_pushw; cc.pf = n_pf; cc.plit = n_plit;
             V4_WT0();
             int cur = entry_rel;
+            while ((cur >> 7) < (warp >> 2) && cur < Wn) cur = E4[cur];
             while ((cur >> 5) < warp && cur < Wn) cur = E[cur];
             uint32_t M = ((cur >> 5) == warp && cur < Wn) ? 1u << (cur & 31) : 0u;
             #pragma unroll
@@ -1335,16 +1398,20 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
             if (lane == 0) c.mbits[warp] = M;
             V4_WTICK(10);
             {   // mcnt[ctx] = marked positions per context (bounds the inserts a record can have missed)
-                const uint32_t cv = marked ? v4_ctx_of(c.key[tid]) : 256u + (uint32_t) lane;
+                const uint32_t cv = marked ? v4_ctx_of(c.key[tid]) : 256u;   // (one group for all unmarked lanes: the match costs per distinct value)
                 const uint32_t grp = __match_any_sync(0xffffffffu, cv);
                 if (marked && (grp >> lane) == 1u) atomicAdd(&c.mcnt[cv], (uint32_t) __popc(grp));
+            }
+            {   // pushw: one atomic per warp and context pushed into
+                const uint32_t c3v = marked ? v4_rb8(c.rbw, (uint32_t) (lo + tid) - 3u) : 256u;
+                const uint32_t grp = __match_any_sync(0xffffffffu, c3v);
+                if (marked && (grp >> lane) == 1u) atomicOr(&c.pushw[c3v], 1u << warp);
             }
             if (marked) {
                 uint32_t c3, pw;
                 v4_push_of(c, (uint32_t) (lo + tid), &c3, &pw);
                 const uint32_t h = v4_pf_hash(c3, pw);
                 atomicOr(&c.pf[h >> 5], 1u << (h & 31u));
-                atomicOr(&c.pushw[c3], 1u << warp);
                 const int t = tid + (int) v4_dec_step(mydec);
                 if (t < Wn) c.plit[t] = v4_dec_kind(mydec) == kV4Lit;
                 else { s_exit = lo + t; s_lastrel = tid; }
