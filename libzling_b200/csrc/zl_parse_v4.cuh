@@ -55,7 +55,7 @@ ZL_HD uint32_t v4_dec_ref(uint32_t d)  { return (d >> 12) & 0x1fffu; }
 ZL_HD uint32_t v4_dec_step(uint32_t d) { const uint32_t k = v4_dec_kind(d); return k == kV4Match ? v4_dec_len(d) : (k == kV4Lit ? 1u : 2u); }
 ZL_HD uint32_t v4_dec_syms(uint32_t d) { return v4_dec_kind(d) == kV4Match ? 2u : 1u; }
 // fx word: frozen slot head (16) | flags << 16
-constexpr uint32_t kV4F_SELF = 1u << 16, kV4F_L1 = 1u << 17, kV4F_L2 = 1u << 18, kV4F_ST = 1u << 19;   // ST: a slot read by the records of x / x+1 / x+2 may be overwritten inside the window
+constexpr uint32_t kV4F_SELF = 1u << 16, kV4F_L1 = 1u << 17, kV4F_L2 = 1u << 18, kV4F_ST = 1u << 19, kV4F_STL = 1u << 20, kV4F_HAZ = 0xfu << 16;   // ST: a slot read by the records of x / x+1 / x+2 may be overwritten inside the window
 
 // host-side statistics of the replay (tests/cxx/parse_v4_sim.cu with -DZL_V4_STATS): loop trip counts of the serial helpers
 #if defined(ZL_V4_STATS)
@@ -502,6 +502,12 @@ ZL_HD void v4_frozen_flags(const V4Ctx& c, int rel) {
             }
         }
         if (st) fl |= kV4F_ST;
+        // the same bound for the records of rel + 1 / rel + 2 whatever the frozen length is (the full probe may run its lazy tests with
+        // another length): information for v4_probe_general only, it does not send the position to the hazard checks
+        for (int q = 1; q <= 2; q++) {
+            const uint32_t hq = c.hdr[rel + q];
+            if ((hq & 31u) && (hq >> 5) + 1u <= c.pcnt[v4_ctx_of(c.key[rel + q])] + 1u) fl |= kV4F_STL;
+        }
     }
     c.fx[rel] = (c.fx[rel] & 0xffffu) | fl;
 }
@@ -700,6 +706,7 @@ ZL_HD bool v4_hazard(const V4Ctx& c, int rel, uint32_t fd, uint32_t fxw, int L2)
     if ((fxw & kV4F_SELF) && v4_link_hazard(c, rel, rel, false)) return true;
     if (nlazy >= 1 && (fxw & kV4F_L1) && v4_link_hazard(c, rel + 1, rel, true)) return true;
     if (nlazy >= 2 && (fxw & kV4F_L2) && v4_link_hazard(c, rel + 2, rel, true)) return true;
+    if (!(fxw & kV4F_ST)) return false;                                  // the static bound already rules the staleness tests out
     const uint32_t h0 = c.hdr[rel];
     if (v4_maybe_stale(c, rel, h0, 0)) {
         const uint32_t cq = v4_ctx_of(c.key[rel]);
@@ -732,7 +739,7 @@ __device__ unsigned long long g_v4prof[16];
 ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t* ref_out) {
     const int x = lo + rel;
     const int D = depth_main(level), L1 = depth_lazy1(level), L2 = depth_lazy2(level);
-    const uint32_t kx = c.key[rel];
+    const uint32_t kx = c.key[rel], fxw = c.fx[rel];
     const uint32_t chk = kx >> 21, cq = v4_ctx_of(kx);
     V4_STAT(4, 1);
     int best = kMinLen - 1, visited = 0, first_pending = -1;
@@ -764,7 +771,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
     int nvis = (int) (hdr & 31u);
     bool stale0 = false;
     uint32_t kc0 = 0;
-    if (v4_maybe_stale(c, rel, hdr, 0)) {
+    if ((fxw & kV4F_ST) && v4_maybe_stale(c, rel, hdr, 0)) {
         kc0 = v4_rank_live(c, rel, cq) + 1u;
         if ((hdr >> 5) + 1u <= kc0) {
             const int nv = v4_valid_nodes(c, rel, nvis, c.cnt[cq] & (kRing - 1), kc0);
@@ -801,7 +808,7 @@ ZL_HD int v4_probe_general(const V4Ctx& c, int lo, int rel, int level, uint32_t*
             const int relz = rel + which;
             const uint32_t hz = c.hdr[relz];
             int nvz = (int) (hz & 31u);
-            if (v4_maybe_stale(c, relz, hz, 1)) {                        // stale lazy record: cut it, or replay when its head is gone
+            if ((fxw & kV4F_STL) && v4_maybe_stale(c, relz, hz, 1)) {    // stale lazy record: cut it, or replay when its head is gone
                 const uint32_t cz = v4_ctx_of(c.key[relz]);
                 const uint32_t kcz = v4_cnt_lazy(c, rel, which);
                 if ((hz >> 5) + 1u <= kcz) {
@@ -1425,7 +1432,7 @@ __global__ void __launch_bounds__(kV4T, 1) zl_rolz_parse_v4_kernel(ParseArgs a, 
                 if (marked && tid >= entry_rel && tid < Wn) {
                     const uint32_t fd = c.fdec[tid], fxw = c.fx[tid];
                     if (level_here != w.level) which = 1;
-                    else if (fxw >> 16) which = 0;
+                    else if (fxw & kV4F_HAZ) which = 0;
                     else if (fd & 511u) nd = v4_dec_match(fd & 511u, (fd >> 18) & (kRing - 1));
                     else which = 2;
                 }
