@@ -212,6 +212,7 @@ def main():
     ap.add_argument("--shard", default="streams", choices=["streams", "stream"], help="streams: one stream per GPU; stream: ONE stream over all GPUs")
     ap.add_argument("--size-mb", type=float, default=100.0)
     ap.add_argument("--level", type=int, default=0)
+    ap.add_argument("--streams", type=int, default=1, help="> 1: that many independent streams of --size-mb each per GPU in ONE batch call (zlb_encode_batch / zlb_decode_batch)")
     ap.add_argument("--skip-parity", action="store_true")
     ap.add_argument("--no-decode", action="store_true", help="skip the secondary decode leg of the encode mode")
     ap.add_argument("--corpus", default="enwik8", choices=["enwik8", "mixed"], help="mixed = BASELINE.json configs[3] (text + binary + random)")
@@ -246,6 +247,9 @@ def main():
             os.environ["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", "nccl_n%d_rank%d.log" % (world, rank))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    if args.streams > 1:
+        run_batch(args, rank, world, local, dist, torch, libzling_b200)
+        return
     if args.mode == "decode":
         run_decode(args, rank, world, local, dist, torch, libzling_b200)
         return
@@ -507,6 +511,89 @@ def run_decode(args, rank, world, local, dist, torch, libzling_b200):
                          "note": "algorithmic bytes = compressed bytes read + decoded bytes written (r + 1 B per unit); the kernel is one serial chain per stream"},
             "cpu_baseline": {"value": round(sample / 1e6 / cpu_dt, 3), "unit": "MB/s", "cores": 1, "kind": cpu_kind,
                              "sample": "decode of the first %d B of the stream once, single thread; %d host cores present" % (sample, os.cpu_count())},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_batch(args, rank, world, local, dist, torch, libzling_b200):
+    """--streams S: S independent streams per GPU through ONE zlb_encode_batch / zlb_decode_batch call (host buffers in and out);
+    every stream is checked against the CPU reference before anything is timed"""
+    nbytes = int(args.size_mb * 1e6)
+    S = args.streams
+    rng_seed = 1000 * rank
+    import libzling_b200.corpus as corpus
+    streams = [corpus.enwik8_shaped(nbytes, seed=rng_seed + 8 + i) if args.corpus == "enwik8" else corpus.mixed(nbytes, seed=rng_seed + 4 + i) for i in range(S)]
+    lib, cpu_kind = cpu_lib()
+    t0 = time.perf_counter()
+    want = [lib.encode(x, args.level) for x in streams]
+    cpu_enc = time.perf_counter() - t0
+    nblocks = S * ((nbytes + BLOCK - 1) // BLOCK)
+    ctx = libzling_b200.Context(device=local, max_blocks=max(nblocks, S))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    if args.mode == "encode":
+        def step():
+            t0 = time.perf_counter()
+            out = ctx.encode_batch(streams, args.level)
+            return out, time.perf_counter() - t0
+        ok = step()[0] == want
+    else:
+        def step():
+            t0 = time.perf_counter()
+            out = ctx.decode_batch(want, [nbytes] * S)
+            return out, time.perf_counter() - t0
+        ok = step()[0] == [x.tobytes() for x in streams]
+    if not ok:
+        raise SystemExit("bench.py: batch output differs from the CPU reference — refusing to report a number")
+    cpu_dt = cpu_enc
+    if args.mode == "decode":
+        t0 = time.perf_counter()
+        for zz in want:
+            lib.decode(zz, nbytes)
+        cpu_dt = time.perf_counter() - t0
+    for _ in range(max(0, args.warmup - 1)):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    times, launches = [], 0
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        barrier()
+        times.append(step()[1])
+        launches += ctx.stats()["launches"]
+    barrier()
+    clocks = sampler.stop()
+    step_s = float(np.mean(times))
+    if dist is not None:
+        t = torch.tensor([step_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_s = float(t[0])
+    value = world * S * nbytes / 1e6 / step_s
+    zbytes = sum(len(z) for z in want)
+    if rank == 0:
+        line = {
+            "metric": METRIC if args.mode == "encode" else METRIC_DEC, "value": round(value, 3), "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "%d independent %s streams of %d B per GPU, level e%d, %s, ONE batch call (zlb_%s_batch), host buffers" % (
+                           S, "enwik8-shaped" if args.corpus == "enwik8" else "mixed", nbytes, args.level, args.mode, args.mode),
+                       "streams_per_gpu": S, "bytes_per_gpu": int(S * nbytes), "level": args.level, "compressed_bytes": int(zbytes), "bit_exact_vs_cpu_reference": True,
+                       "l2": "256 MB buffer written between timed steps (L2 flush)", "lib_sha16": lib_sha16()},
+            "e2e": {"value": round(value, 3), "unit": "MB/s", "h2d_bytes_per_step": int(S * nbytes if args.mode == "encode" else zbytes),
+                    "d2h_bytes_per_step": int(zbytes if args.mode == "encode" else S * nbytes), "ms_per_step": round(step_s * 1e3, 3),
+                    "timing": "host wall clock around the batch call (pageable host buffers in and out), max over ranks"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": {"value": round(S * nbytes / 1e6 / cpu_dt, 3), "unit": "MB/s", "cores": 1, "kind": cpu_kind,
+                             "sample": "the same %d streams once, one after the other, single thread; %d host cores present" % (S, os.cpu_count())},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

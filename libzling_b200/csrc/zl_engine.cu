@@ -36,6 +36,8 @@ enum { EV_START, EV_H2D, EV_PARSE0, EV_PARSE1, EV_MTF1, EV_BUILD1, EV_PACK0, EV_
 
 struct zlb_ctx {
     int device = 0, max_blocks = 0;
+    int max_clusters[5][5];         // [level][log2 size]: clusters of that size the GPU holds at once (-1 = not asked yet)
+    int stats_cluster = 1;          // cluster size of the last parse launch
     uint32_t spec_reparsed = 0;     // blocks re-parsed by the last speculative completion (sharded streams)
     cudaStream_t stream = nullptr;
     // device
@@ -203,6 +205,7 @@ zlb_ctx* zlb_create(int device, int max_blocks) {
     zlb_ctx* c = new (std::nothrow) zlb_ctx();
     if (!c) { fail(ZLB_E_NOMEM, "zlb_create: out of host memory"); return nullptr; }
     c->device = device; c->max_blocks = max_blocks;
+    for (auto& row : c->max_clusters) for (int& v : row) v = -1;
     if (ctx_alloc(c) != ZLB_OK) { zlb_destroy(c); return nullptr; }
     return c;
 }
@@ -326,14 +329,42 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
             {
                 // one CTA per block, or a cluster of CTAs per block (helpers take the chain walks, zl_parse_v4.cuh) while the clusters
                 // of all blocks of the call still fit the GPU at once
+                // (the largest cluster of which the GPU can hold one per block that is parsed in this pass: asked from the occupancy
+                // calculator once per level and size — a 16-CTA cluster needs 16 free SMs inside one GPC)
                 int cl = c->parse_cluster;
-                if (cl <= 0) cl = nb * 8 <= 120 ? 8 : (nb * 4 <= 120 ? 4 : (nb * 2 <= 120 ? 2 : 1));
                 cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned) (nb * cl)); cfg.blockDim = dim3(kV4T); cfg.dynamicSmemBytes = (size_t) lay.total; cfg.stream = st;
+                cfg.blockDim = dim3(kV4T); cfg.dynamicSmemBytes = (size_t) lay.total; cfg.stream = st;
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = (unsigned) cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
+                if (cl <= 0) {
+                    int n_active = 0;
+                    for (int b = 0; b < nb; b++) n_active += c->h_active[b] != 0;
+                    const int lv = level < 0 ? 0 : (level > 4 ? 4 : level);
+                    cl = 1;
+                    for (int k = 4; k >= 1 && cl == 1; k--) {             // 16, 8, 4, 2
+                        int& cap = c->max_clusters[lv][k];
+                        if (cap < 0) {
+                            cap = 0;
+                            attr[0].val.clusterDim.x = 1u << k; cfg.gridDim = dim3(1u << k);
+                            int n = 0;
+                            cudaError_t qe;
+                            switch (lv) {
+                                case 0:  qe = cudaOccupancyMaxActiveClusters(&n, zl_rolz_parse_v4_kernel<2, 1>, &cfg); break;
+                                case 1:  qe = cudaOccupancyMaxActiveClusters(&n, zl_rolz_parse_v4_kernel<4, 1>, &cfg); break;
+                                case 2:  qe = cudaOccupancyMaxActiveClusters(&n, zl_rolz_parse_v4_kernel<6, 2>, &cfg); break;
+                                case 3:  qe = cudaOccupancyMaxActiveClusters(&n, zl_rolz_parse_v4_kernel<8, 3>, &cfg); break;
+                                default: qe = cudaOccupancyMaxActiveClusters(&n, zl_rolz_parse_v4_kernel<16, 4>, &cfg); break;
+                            }
+                            if (qe == cudaSuccess) cap = n; else cudaGetLastError();
+                        }
+                        if (cap >= n_active && n_active > 0) cl = 1 << k;
+                    }
+                }
+                attr[0].val.clusterDim.x = (unsigned) cl;
+                cfg.gridDim = dim3((unsigned) (nb * cl));
+                c->stats_cluster = cl;
                 switch (level) {                                  // (depth, lazy depth) of the requested level, src/libzling_lz.cpp:129-135
                     case 0:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<2, 1>, pa, level, c->d_v4c)); break;
                     case 1:  CU(cudaLaunchKernelEx(&cfg, zl_rolz_parse_v4_kernel<4, 1>, pa, level, c->d_v4c)); break;
@@ -458,6 +489,9 @@ static int encode_ranges(zlb_ctx* c, int level, const uint8_t* d_in, int nb, Enc
         c->stats.cyc_total = c->h_v4c.cyc_total; c->stats.cyc_orbit = c->h_v4c.cyc_orbit; c->stats.cyc_rank = c->h_v4c.cyc_rank;
         c->stats.cyc_decide = c->h_v4c.cyc_decide;
         if (getenv("ZLB_V4_TRACE")) {
+            fprintf(stderr, "v4 cluster size %d (GPU holds", c->stats_cluster);
+            for (int k = 1; k <= 4; k++) fprintf(stderr, " %d x %d", c->max_clusters[level < 0 ? 0 : (level > 4 ? 4 : level)][k], 1 << k);
+            fprintf(stderr, ")\n");
             fprintf(stderr, "v4 phases (cycles per window, summed over blocks / windows):");
             for (int i = 0; i < 40; i++) fprintf(stderr, " ph%d=%.0f", i, (double) c->h_v4c.ph[i] / (double) (c->h_v4c.windows ? c->h_v4c.windows : 1));
             fprintf(stderr, "\n");
