@@ -86,11 +86,12 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 struct Gpu {
     zlb_ctx* ctx = nullptr;
     unsigned char* pin_in = nullptr;     // page-locked staging: max_blocks * 16 MiB
+    unsigned char* pin_in2 = nullptr;    // large tier only: the second input buffer of the streaming pipeline (Encode)
     unsigned char* pin_out = nullptr;    // page-locked staging: zlb_encode_bound of the above
     size_t in_cap = 0, out_cap = 0;
     int max_blocks = 0;
     ~Gpu() {
-        zlb_host_free(pin_in); zlb_host_free(pin_out);
+        zlb_host_free(pin_in); zlb_host_free(pin_in2); zlb_host_free(pin_out);
         zlb_destroy(ctx);
     }
 };
@@ -115,7 +116,8 @@ public:
         g->out_cap = zlb_encode_bound(g->in_cap);
         g->pin_in = (unsigned char*) zlb_host_alloc(g->in_cap + 64);
         g->pin_out = (unsigned char*) zlb_host_alloc(g->out_cap + 64);
-        if (!g->pin_in || !g->pin_out) throw std::bad_alloc();
+        if (large) g->pin_in2 = (unsigned char*) zlb_host_alloc(g->in_cap + 64);
+        if (!g->pin_in || !g->pin_out || (large && !g->pin_in2)) throw std::bad_alloc();
         return g.release();
     }
     void release(Gpu* g) {
@@ -146,6 +148,11 @@ struct EncoderGuard {
     zlb_encoder* e;
     explicit EncoderGuard(zlb_encoder* e_) : e(e_) {}
     ~EncoderGuard() { zlb_encoder_end(e); }
+};
+struct PendingGuard {                    // a submitted batch must not stay pending on a context that goes back to the pool
+    zlb_encoder*& e; Gpu*& g; bool armed = false;
+    PendingGuard(zlb_encoder*& e_, Gpu*& g_) : e(e_), g(g_) {}
+    ~PendingGuard() { if (armed && e) { size_t n = 0; zlb_encode_complete(e, g->pin_out, g->out_cap, &n); } }
 };
 struct DecoderGuard {
     zlb_decoder* d;
@@ -179,35 +186,16 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
     if (!enc.e) raise_zlb(ZLB_E_CUDA);
 
     bool io_error = false;
-    bool upgraded = false;
-    size_t carried = 0;                          // bytes already read into the small context's staging when the input turned out longer
-    while (!io_error && !inputter->IsEnd() && !inputter->IsErr()) {
-        // fill up to max_blocks blocks; every block except the stream's last is exactly 16 MiB (libzling.cpp:193-196)
-        size_t have = carried;
-        carried = 0;
-        while (have < lease.g->in_cap && !inputter->IsEnd() && !inputter->IsErr()) {
-            have += inputter->GetData(lease.g->pin_in + have, lease.g->in_cap - have);
+    // pull bytes until the buffer is full or the input ends; every block except the stream's last is exactly 16 MiB (libzling.cpp:193-196)
+    auto fill = [&](unsigned char* buf, size_t have, size_t cap) {
+        while (have < cap && !inputter->IsEnd() && !inputter->IsErr()) {
+            have += inputter->GetData(buf + have, cap - have);
             if (inputter->IsErr()) { io_error = true; break; }
         }
-        if (io_error || have == 0) break;
-        if (!upgraded && lease.g->max_blocks == 1 && have == lease.g->in_cap && !inputter->IsEnd()) {
-            upgraded = true;
-            // longer than one block: move to the large context (the encoder holds no stream state yet) and keep reading
-            std::vector<unsigned char> first(lease.g->pin_in, lease.g->pin_in + have);
-            zlb_encoder_end(enc.e); enc.e = nullptr;
-            lease.upgrade();
-            enc.e = zlb_encoder_begin(lease.g->ctx, level);
-            if (!enc.e) raise_zlb(ZLB_E_CUDA);
-            memcpy(lease.g->pin_in, first.data(), have);
-            carried = have;
-            continue;
-        }
-        Gpu& g = *lease.g;
-        size_t produced = 0;
-        const int rc = zlb_encode_blocks(enc.e, g.pin_in, have, g.pin_out, g.out_cap, &produced);
-        if (rc != ZLB_OK) raise_zlb(rc);
-
-        // hand the frames to the outputter block by block so that OnProcess keeps its place in the order
+        return have;
+    };
+    // hand the frames of one batch to the outputter block by block so that OnProcess keeps its place in the order
+    auto emit = [&](Gpu& g, unsigned char* in, size_t have) {
         size_t at = 0;
         for (size_t boff = 0; boff < have && !io_error; boff += ZLB_BLOCK_BYTES) {
             const size_t blen = have - boff < ZLB_BLOCK_BYTES ? have - boff : (size_t) ZLB_BLOCK_BYTES;
@@ -219,7 +207,48 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
             end += 1;
             if (!put_all(outputter, g.pin_out + at, end - at)) { io_error = true; break; }
             at = end;
-            if (action_handler) action_handler->OnProcess(g.pin_in + boff, blen);
+            if (action_handler) action_handler->OnProcess(in + boff, blen);
+        }
+    };
+
+    size_t have = fill(lease.g->pin_in, 0, lease.g->in_cap);
+    if (!io_error && have == lease.g->in_cap && !inputter->IsEnd()) {
+        // longer than one block: move to the large context (the encoder holds no stream state yet) and keep reading
+        std::vector<unsigned char> first(lease.g->pin_in, lease.g->pin_in + have);
+        zlb_encoder_end(enc.e); enc.e = nullptr;
+        lease.upgrade();
+        enc.e = zlb_encoder_begin(lease.g->ctx, level);
+        if (!enc.e) raise_zlb(ZLB_E_CUDA);
+        memcpy(lease.g->pin_in, first.data(), have);
+        have = fill(lease.g->pin_in, have, lease.g->in_cap);
+    }
+    // Streaming pipeline (two page-locked input buffers): the parse of a batch is launched without waiting for it
+    // (zlb_encode_submit), the next batch is read from the Inputter while it runs, and the frames of a finished batch go to the
+    // Outputter while the next one is already on the GPU.  All Inputter / Outputter / handler calls stay on this thread.
+    PendingGuard pending(enc.e, lease.g);
+    unsigned char* bufs[2] = { lease.g->pin_in, lease.g->pin_in2 };
+    int cur = 0;
+    if (!io_error && have > 0) {
+        int rc = zlb_encode_submit(enc.e, bufs[cur], have);
+        if (rc != ZLB_OK) raise_zlb(rc);
+        pending.armed = true;
+        while (true) {
+            Gpu& g = *lease.g;
+            size_t have_next = 0;
+            if (bufs[cur ^ 1] && !inputter->IsEnd() && !inputter->IsErr()) have_next = fill(bufs[cur ^ 1], 0, g.in_cap);
+            size_t produced = 0;
+            pending.armed = false;
+            rc = zlb_encode_complete(enc.e, g.pin_out, g.out_cap, &produced);
+            if (rc != ZLB_OK) raise_zlb(rc);
+            if (!io_error && have_next > 0) {
+                rc = zlb_encode_submit(enc.e, bufs[cur ^ 1], have_next);
+                if (rc != ZLB_OK) raise_zlb(rc);
+                pending.armed = true;
+            }
+            emit(g, bufs[cur], have);
+            if (io_error || have_next == 0) break;
+            cur ^= 1;
+            have = have_next;
         }
     }
     if (action_handler) action_handler->OnDone();

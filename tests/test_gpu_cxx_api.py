@@ -42,6 +42,28 @@ def test_cxx_encode_decode(cli, oracle):
             assert back.read_bytes() == data, (name, level)
 
 
+def test_cxx_streaming_pipeline(cli, oracle):
+    """an input of several batches (ZLING_B200_BLOCKS=2: batches of two blocks) goes through the streaming pipeline of the driver — the
+    next batch is read while the current one is parsed, frames are written while the next one runs — and must still be the
+    reference's bytes, with OnProcess called once per block in order; also with an input that ends exactly at a batch boundary"""
+    import numpy as np
+    from libzling_b200 import corpus
+    exe, d = cli
+    env = dict(os.environ, ZLING_B200_BLOCKS="2")
+    for nbytes, level in ((4 * (1 << 24) + 12345, 0), (4 * (1 << 24), 2)):
+        rng = np.random.default_rng(5)
+        data = np.concatenate([corpus.enwik8_shaped(nbytes - (3 << 20), seed=21), rng.integers(0, 256, 3 << 20, dtype=np.uint8)]).tobytes()
+        src, z, back = d / "big.bin", d / "big.zl", d / "big.out"
+        src.write_bytes(data)
+        r = subprocess.run([exe, "e%d" % level, str(src), str(z)], capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert z.read_bytes() == oracle.encode(data, level), (nbytes, level)
+        assert b"blocks=%d" % ((len(data) + (1 << 24) - 1) >> 24) in r.stderr, r.stderr
+        r = subprocess.run([exe, "d", str(z), str(back)], capture_output=True, env=env)
+        assert r.returncode == 0, r.stderr
+        assert back.read_bytes() == data
+
+
 def test_cxx_decode_malformed_throws(cli, oracle):
     exe, d = cli
     z = bytearray(oracle.encode(b"hello " * 50, 0))
