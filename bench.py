@@ -60,6 +60,13 @@ def lib_sha16():
         return hashlib.sha256(f.read()).hexdigest()[:16]
 
 
+def src_sha16():
+    """the library's SOURCES (the nvcc build is not bit-reproducible, the sources are).  None when a source is newer than the library
+    that is loaded (then the hash would not describe what runs)"""
+    from libzling_b200 import build as zbuild
+    return None if zbuild.needs_build() else zbuild.source_sha16()
+
+
 def load_traffic(kernel, nbytes, level):
     """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` from a committed `ncu --set full` capture
     (profiles/traffic_<kernel>.json, written by scripts/ncu_traffic.py); accepted only for the workload it was captured
@@ -68,9 +75,10 @@ def load_traffic(kernel, nbytes, level):
     if os.path.exists(p):
         with open(p) as f:
             t = json.load(f)
-        if int(t.get("workload_bytes", -1)) == int(nbytes) and int(t.get("level", -1)) == int(level) and t.get("lib_sha16") == lib_sha16():
+        same_code = t.get("lib_sha16") == lib_sha16() or (t.get("src_sha16") is not None and t.get("src_sha16") == src_sha16())
+        if int(t.get("workload_bytes", -1)) == int(nbytes) and int(t.get("level", -1)) == int(level) and same_code:
             return int(t["dram_bytes_read"] + t["dram_bytes_write"]), t.get("source")
-        return None, "the capture in profiles/ is for another build or workload (lib %s, now %s): not used" % (t.get("lib_sha16"), lib_sha16())
+        return None, "the capture in profiles/ is for another build or workload (sources %s, now %s): not used" % (t.get("src_sha16"), src_sha16())
     return None, None
 
 
@@ -415,7 +423,7 @@ def main():
                        "compressed_bytes": int(comp_len), "ratio": round(comp_len / max(whole.size if want is not None else nlocal, 1), 4),
                        "bit_exact_vs_cpu_reference": not args.skip_parity,
                        "l2": "256 MB buffer written between timed steps (L2 flush); working set (input + 12 MB bucket state/block + tokens) exceeds L2",
-                       "parse_kernel": "zl_rolz_parse_v%s" % os.environ.get("ZLB_PARSE", "4"), "shard": args.shard, "lib_sha16": lib_sha16()},
+                       "parse_kernel": "zl_rolz_parse_v%s" % os.environ.get("ZLB_PARSE", "4"), "shard": args.shard, "lib_sha16": lib_sha16(), "src_sha16": src_sha16()},
             "e2e": {"value": round(e2e_value, 3), "unit": "MB/s", "h2d_bytes_per_step": int(nlocal), "d2h_bytes_per_step": int(n),
                     "ms_per_step": round(e2e_step * 1e3, 3),
                     "timing": "host wall clock around zlb_encoder_begin -> %s -> zlb_encoder_end, pinned host buffers, max over ranks"

@@ -20,6 +20,17 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def source_sha16():
+    """sha256 prefix over the sources the library is built from (the build itself is not bit-reproducible: nvcc embeds temporary
+    names), in a fixed order: identifies the CODE a measurement was taken from"""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        with open(os.path.join(CSRC, d), "rb") as f:
+            h.update(d.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

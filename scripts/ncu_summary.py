@@ -14,7 +14,10 @@ import subprocess
 import sys
 
 rep, out = sys.argv[1], sys.argv[2]
-sha = sys.argv[3] if len(sys.argv) > 3 else None
+sha = sys.argv[3] if len(sys.argv) > 3 else None          # "<lib sha16>[:<source sha16>]"
+src_sha = None
+if sha and ":" in sha:
+    sha, src_sha = sha.split(":", 1)
 wbytes = int(sys.argv[4]) if len(sys.argv) > 4 else None
 level = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -47,6 +50,6 @@ with open(out, "w", newline="") as f:
             seen.add(name)
             short = name.split("<")[0]
             with open(os.path.join(os.path.dirname(out), "traffic_%s.json" % short), "w") as g:
-                json.dump({"kernel": name, "lib_sha16": sha, "workload_bytes": wbytes, "level": level, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+                json.dump({"kernel": name, "lib_sha16": sha, "src_sha16": src_sha, "workload_bytes": wbytes, "level": level, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                            "duration_ms": round(dur, 4), "source": "%s (ncu --set full --clock-control none, first launch of the kernel)" % os.path.basename(out)}, g, indent=1)
 print("wrote", out)
