@@ -33,7 +33,8 @@ want = [w for w in want if w in col]
 
 def scale(v, u):
     v = float(v.replace(",", ""))
-    return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "usecond": 1e-3, "msecond": 1, "second": 1e3, "nsecond": 1e-6}.get(u, 1)
+    return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1, "usecond": 1e-3, "msecond": 1, "second": 1e3, "nsecond": 1e-6,
+                    "us": 1e-3, "ms": 1, "s": 1e3, "ns": 1e-6}.get(u, 1)
 
 
 with open(out, "w", newline="") as f:
