@@ -32,3 +32,27 @@ def test_gpu_arm_refuses_to_run_without_a_gpu():
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) or "no CPU" in (r.stderr + r.stdout)
+
+
+def test_traffic_figure_is_tied_to_the_sources(tmp_path, monkeypatch):
+    """roofline.traffic comes from a committed ncu capture and is used only for the workload it was taken on and for the code it
+    was taken from (sha of the library, or — the nvcc build is not bit-reproducible — sha of its sources)"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from libzling_b200 import build as zbuild
+    src = zbuild.source_sha16()
+    assert len(src) == 16 and src == zbuild.source_sha16()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "lib_sha16", lambda: "0" * 16)
+    monkeypatch.setattr(bench, "src_sha16", lambda: src)
+    os.makedirs(tmp_path / "profiles")
+    rec = {"kernel": "k", "lib_sha16": "f" * 16, "src_sha16": src, "workload_bytes": 100, "level": 0, "dram_bytes_read": 7, "dram_bytes_write": 5, "source": "x"}
+    (tmp_path / "profiles" / "traffic_k.json").write_text(json.dumps(rec))
+    assert bench.load_traffic("k", 100, 0) == (12, "x")                       # same sources
+    assert bench.load_traffic("k", 101, 0)[0] is None                         # another workload
+    assert bench.load_traffic("k", 100, 4)[0] is None                         # another level
+    monkeypatch.setattr(bench, "src_sha16", lambda: "1" * 16)
+    assert bench.load_traffic("k", 100, 0)[0] is None                         # other sources
+    monkeypatch.setattr(bench, "lib_sha16", lambda: "f" * 16)
+    assert bench.load_traffic("k", 100, 0)[0] == 12                           # the very library of the capture
+    assert bench.load_traffic("none", 100, 0) == (None, None)
