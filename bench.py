@@ -217,7 +217,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="encode", choices=["encode", "decode"])
-    ap.add_argument("--shard", default="streams", choices=["streams", "stream"], help="streams: one stream per GPU; stream: ONE stream over all GPUs")
+    ap.add_argument("--shard", default=None, choices=["streams", "stream"],
+                    help="streams: one stream per GPU (default); stream: ONE stream over all GPUs (default for BASELINE.json configs[3]: --corpus mixed --size-mb 1000)")
     ap.add_argument("--size-mb", type=float, default=100.0)
     ap.add_argument("--level", type=int, default=0)
     ap.add_argument("--streams", type=int, default=1, help="> 1: that many independent streams of --size-mb each per GPU in ONE batch call (zlb_encode_batch / zlb_decode_batch)")
@@ -225,6 +226,8 @@ def main():
     ap.add_argument("--no-decode", action="store_true", help="skip the secondary decode leg of the encode mode")
     ap.add_argument("--corpus", default="enwik8", choices=["enwik8", "mixed"], help="mixed = BASELINE.json configs[3] (text + binary + random)")
     args = ap.parse_args()
+    if args.shard is None:
+        args.shard = "stream" if (args.corpus == "mixed" and args.size_mb >= 1000 and args.mode == "encode" and args.streams == 1) else "streams"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

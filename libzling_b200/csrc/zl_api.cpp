@@ -9,6 +9,8 @@
 // Batching: without an ActionHandler several blocks go to the GPU per call (unobservable); with one, encode still
 // batches (the handler only ever sees blocks after their bytes were emitted, in order) but decode proceeds one
 // block at a time because a handler may read from the Inputter inside OnProcess (demo/zling.cpp:124-132).
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -74,6 +76,15 @@ size_t FileOutputter::GetOutputSize() { return m_total_write; }
 // small input never pays for the large buffers.  ZLING_B200_DEVICE selects the GPU.
 namespace {
 
+// ZLING_B200_TRACE=1: wall-clock marks of the driver's phases on stderr (where does a CLI run spend its time?)
+void trace(const char* what, size_t n = 0) {
+    static const bool on = getenv("ZLING_B200_TRACE") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "[zling-b200 %9.1f ms] %s %zu\n", ms, what, n);
+}
+
 int env_int(const char* name, int dflt, int lo, int hi) {
     const char* v = getenv(name);
     if (!v || !*v) return dflt;
@@ -116,8 +127,7 @@ public:
         g->out_cap = zlb_encode_bound(g->in_cap);
         g->pin_in = (unsigned char*) zlb_host_alloc(g->in_cap + 64);
         g->pin_out = (unsigned char*) zlb_host_alloc(g->out_cap + 64);
-        if (large) g->pin_in2 = (unsigned char*) zlb_host_alloc(g->in_cap + 64);
-        if (!g->pin_in || !g->pin_out || (large && !g->pin_in2)) throw std::bad_alloc();
+        if (!g->pin_in || !g->pin_out) throw std::bad_alloc();      // (pin_in2 is allocated by the first Encode that needs a second batch)
         return g.release();
     }
     void release(Gpu* g) {
@@ -177,7 +187,9 @@ bool put_all(Outputter* out, unsigned char* p, size_t len) {
 // ---- src/libzling.cpp:174-291 -------------------------------------------------------------------------------
 int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handler, int level) {
     if (level < 0 || level > 4) return -1;       // the reference never terminates here; see libzling.h
+    trace("Encode: enter");
     GpuLease lease(false);                       // acquired before OnInit: a call that cannot get a GPU throws without having started
+    trace("Encode: context ready");
     if (action_handler) {
         action_handler->SetInputterOutputter(inputter, outputter, true);
         action_handler->OnInit();
@@ -212,6 +224,7 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
     };
 
     size_t have = fill(lease.g->pin_in, 0, lease.g->in_cap);
+    trace("Encode: first block read", have);
     if (!io_error && have == lease.g->in_cap && !inputter->IsEnd()) {
         // longer than one block: move to the large context (the encoder holds no stream state yet) and keep reading
         std::vector<unsigned char> first(lease.g->pin_in, lease.g->pin_in + have);
@@ -220,7 +233,9 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
         enc.e = zlb_encoder_begin(lease.g->ctx, level);
         if (!enc.e) raise_zlb(ZLB_E_CUDA);
         memcpy(lease.g->pin_in, first.data(), have);
+        trace("Encode: large context ready");
         have = fill(lease.g->pin_in, have, lease.g->in_cap);
+        trace("Encode: first batch read", have);
     }
     // Streaming pipeline (two page-locked input buffers): the parse of a batch is launched without waiting for it
     // (zlb_encode_submit), the next batch is read from the Inputter while it runs, and the frames of a finished batch go to the
@@ -235,17 +250,27 @@ int Encode(Inputter* inputter, Outputter* outputter, ActionHandler* action_handl
         while (true) {
             Gpu& g = *lease.g;
             size_t have_next = 0;
-            if (bufs[cur ^ 1] && !inputter->IsEnd() && !inputter->IsErr()) have_next = fill(bufs[cur ^ 1], 0, g.in_cap);
+            if (g.max_blocks > 1 && !inputter->IsEnd() && !inputter->IsErr()) {
+                if (!g.pin_in2) {                 // second staging buffer: only streams of more than one batch pay for it
+                    g.pin_in2 = (unsigned char*) zlb_host_alloc(g.in_cap + 64);
+                    if (!g.pin_in2) throw std::bad_alloc();
+                    bufs[1] = g.pin_in2;
+                }
+                have_next = fill(bufs[cur ^ 1], 0, g.in_cap);
+            }
             size_t produced = 0;
             pending.armed = false;
+            trace("Encode: next batch read", have_next);
             rc = zlb_encode_complete(enc.e, g.pin_out, g.out_cap, &produced);
             if (rc != ZLB_OK) raise_zlb(rc);
+            trace("Encode: batch complete", produced);
             if (!io_error && have_next > 0) {
                 rc = zlb_encode_submit(enc.e, bufs[cur ^ 1], have_next);
                 if (rc != ZLB_OK) raise_zlb(rc);
                 pending.armed = true;
             }
             emit(g, bufs[cur], have);
+            trace("Encode: batch written", have);
             if (io_error || have_next == 0) break;
             cur ^= 1;
             have = have_next;
