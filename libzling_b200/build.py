@@ -20,12 +20,16 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+# what runs on the device and how it is launched (the C++ driver above the C ABI and the public headers cannot change a kernel's traffic)
+DEVICE_DEPS = ["zl_engine.cu", "zl_kernels.cu", "zl_kernels.cuh", "zl_parse_v4.cuh", "zl_mtf_walk.h", "zl_shard.cuh", "zl_tables.h"]
+
+
 def source_sha16():
-    """sha256 prefix over the sources the library is built from (the build itself is not bit-reproducible: nvcc embeds temporary
-    names), in a fixed order: identifies the CODE a measurement was taken from"""
+    """sha256 prefix over the device-side sources of the library (the build itself is not bit-reproducible: nvcc embeds temporary
+    names), in a fixed order: identifies the CODE a kernel measurement was taken from"""
     import hashlib
     h = hashlib.sha256()
-    for d in sorted(DEPS):
+    for d in sorted(DEVICE_DEPS):
         with open(os.path.join(CSRC, d), "rb") as f:
             h.update(d.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
